@@ -1,0 +1,170 @@
+/*
+ * sopht_b200.h -- C ABI of libsophtb200.so
+ *
+ * B200-native (sm_100a) implementation of the per-timestep Eulerian/Lagrangian
+ * hot path of sopht-mpi.  The reference (pure Python: pystencils / numba /
+ * mpi4py-fft JITs) has no FFI; the boundary a maintainer binds is its Python
+ * operator API.  Each entry point below names the reference callable it
+ * replaces (paths relative to the reference tree, sopht_mpi/...).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative value on error;
+ *    sb200_last_error() returns a message for the calling thread.
+ *  - all field pointers are DEVICE pointers (owned by the caller, e.g. a torch
+ *    tensor); `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *  - fields are C-ordered (z,y,x) / (ncomp,z,y,x), padded with `gs` ghost
+ *    cells on every side of every axis, exactly the reference's local arrays
+ *    (simulator/flow/flow_simulators_mpi_3d.py:170-196).  2D: (y,x), n[0] = 1.
+ *  - no torch / C++ types cross this boundary.
+ */
+#ifndef SOPHT_B200_H
+#define SOPHT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_F32 0
+#define SB200_F64 1
+
+/* local (per rank / per GPU) grid description */
+typedef struct sb200_grid {
+  int32_t dim;     /* 2 or 3 */
+  int32_t dtype;   /* SB200_F32 / SB200_F64 */
+  int32_t gs;      /* ghost size */
+  int32_t n[3];    /* local interior size (z,y,x); 2D: n[0] = 1 */
+  int32_t phys[6]; /* z_prev,z_next,y_prev,y_next,x_prev,x_next: 1 = neighbour is
+                      PROC_NULL (physical boundary), utils/mpi_utils_3d.py:70-74 */
+} sb200_grid_t;
+
+const char* sb200_last_error(void);
+int sb200_version(void);
+
+/* ---- pointwise ops over `count` contiguous reals (whole padded arrays) ----
+ * replace the un-vendored sopht elementwise kernels called at
+ * simulator/flow/flow_simulators_mpi_3d.py:267-269,303-318,397-401,422-424 and
+ * numeric/eulerian_grid_ops/stencil_ops_3d/laplacian_filter_mpi_3d.py:102-107 */
+int sb200_set_fixed_val(int dtype, void* field, int64_t count, double value, void* stream);
+int sb200_elementwise_sum(int dtype, void* sum, const void* a, const void* b, int64_t count, void* stream);
+int sb200_elementwise_copy(int dtype, void* dst, const void* src, int64_t count, void* stream);
+int sb200_elementwise_saxpby(int dtype, void* sum, const void* a, double pa, const void* b, double pb,
+                             int64_t count, void* stream);
+/* result/field_1/field_2 are (3,count) */
+int sb200_elementwise_cross_product(int dtype, void* result, const void* f1, const void* f2,
+                                    int64_t count, void* stream);
+/* field (ncomp,count) += vals[c] */
+int sb200_add_fixed_val(int dtype, void* field, int ncomp, int64_t count, const double* vals, void* stream);
+
+/* ---- stencils: interior + six boundary slabs + physical-ring zeroing ------ */
+/* stencil_ops_3d/update_vorticity_from_velocity_forcing_mpi_3d.py:27-176 and
+ * stencil_ops_2d/update_vorticity_from_velocity_forcing_mpi_2d.py:8-123
+ * (3D: omega(3), F(3); 2D: omega scalar, F(2)) */
+int sb200_update_vorticity_from_velocity_forcing(const sb200_grid_t* g, void* vorticity,
+                                                 const void* velocity_forcing, double prefactor, void* stream);
+/* stencil_ops_3d/curl_mpi_3d.py:29-194; 2D: stencil_ops_2d/outplane_field_curl_mpi_2d.py:10-141 */
+int sb200_curl(const sb200_grid_t* g, void* curl, const void* field, double prefactor, void* stream);
+/* stencil_ops_3d/diffusion_flux_mpi_3d.py:35-192 (scalar field) */
+int sb200_diffusion_flux(const sb200_grid_t* g, void* diffusion_flux, const void* field, double prefactor,
+                         void* stream);
+/* stencil_ops_3d/diffusion_timestep_mpi_3d.py:41-90: ncomp sequential scalar
+ * steps sharing one scalar flux buffer */
+int sb200_diffusion_timestep(const sb200_grid_t* g, void* field, int ncomp, void* diffusion_flux,
+                             double nu_dt_by_dx2, void* stream);
+/* stencil_ops_3d/advection_flux_mpi_3d.py:25-193 (ENO3, kernel support 2) */
+int sb200_advection_flux_eno3(const sb200_grid_t* g, void* advection_flux, const void* field,
+                              const void* velocity, double inv_dx, void* stream);
+/* stencil_ops_3d/advection_timestep_mpi_3d.py:40-93 */
+int sb200_advection_timestep_eno3(const sb200_grid_t* g, void* field, int ncomp, void* advection_flux,
+                                  const void* velocity, double dt_by_dx, void* stream);
+/* stencil_ops_3d/divergence_mpi_3d.py:31-198 */
+int sb200_divergence(const sb200_grid_t* g, void* divergence, const void* field, double inv_dx, void* stream);
+/* stencil_ops_3d/laplacian_filter_mpi_3d.py:267-419; filter_type 0 = multiplicative, 1 = convolution */
+int sb200_laplacian_filter(const sb200_grid_t* g, void* field, int ncomp, int filter_order, int filter_type,
+                           void* filter_flux_buffer, void* field_buffer, void* stream);
+/* stencil_ops_3d/penalise_field_boundary_mpi_3d.py:185-267.  `factors` is a
+ * DEVICE array [2*dim][gs+width] of the sine factors in real_t, ordered
+ * (3D) z_front,z_back,y_front,y_back,x_front,x_back, each indexed by the
+ * distance-ordered position inside its slab (index 0 = outermost ghost cell
+ * for *_front, = first slab cell for *_back, i.e. array order). */
+int sb200_penalise_field_boundary(const sb200_grid_t* g, void* field, int ncomp, int width,
+                                  const void* factors, void* stream);
+
+/* ---- reductions over the interior; result written as ONE double at `out`
+ * (device pointer, 8 bytes) ------------------------------------------------ */
+/* max over interior of sum_c |u_c| : simulator/flow/flow_simulators_mpi_3d.py:429-442 */
+int sb200_max_abs_sum(const sb200_grid_t* g, const void* field, int ncomp, void* out, void* stream);
+/* signed max over interior of all components: flow_simulators_mpi_3d.py:471-476 */
+int sb200_max(const sb200_grid_t* g, const void* field, int ncomp, void* out, void* stream);
+/* sum of squares over interior: flow_simulators_mpi_3d.py:461-464 */
+int sb200_sum_squares(const sb200_grid_t* g, const void* field, int ncomp, void* out, void* stream);
+
+/* ---- fused hot path -------------------------------------------------------
+ * u = prefactor*curl(psi), zero physical ring, u += U_inf, F = 0 and
+ * max_abs_sum(u) in one sweep: flow_simulators_mpi_3d.py:388-393,422-424,429-442.
+ * `forcing` may be NULL, `max_out` may be NULL. */
+int sb200_velocity_from_stream_function(const sb200_grid_t* g, void* velocity, const void* stream_func,
+                                        double prefactor, const double* free_stream, void* forcing,
+                                        void* max_out, void* stream);
+/* omega <- omega + p*curl(F); omega <- omega + p*curl(u x omega); omega <- omega + c*lap(omega)
+ * flow_simulators_mpi_3d.py:395-411,416-420 in one streaming pass.
+ * `forcing` may be NULL (flow_type "navier_stokes"); `out` must not alias `vorticity`. */
+int sb200_vorticity_rhs_fused_3d(const sb200_grid_t* g, void* out, const void* vorticity,
+                                 const void* velocity, const void* forcing, double curl_prefactor,
+                                 double nu_dt_by_dx2, void* stream);
+
+/* ---- unbounded Poisson solver ---------------------------------------------
+ * poisson_solver_3d/UnboundedPoissonSolverMPI3D.py:22-187 (+ fft_mpi_3d.py),
+ * poisson_solver_2d/UnboundedPoissonSolverMPI2D.py:12-153.
+ * nz,ny,nx: GLOBAL interior grid; this handle serves rank `rank` of `nranks`
+ * z-slabs (y-slabs in 2D).  With nranks > 1 the caller performs the two
+ * transposes between sb200_poisson_forward_local / _backward_local. */
+typedef struct sb200_poisson sb200_poisson_t;
+int sb200_poisson_create(sb200_poisson_t** out, int dim, int dtype, int nz, int ny, int nx, int gs,
+                         double x_range, int rank, int nranks, int backend, void* stream);
+int sb200_poisson_destroy(sb200_poisson_t* p);
+/* single-rank solve of `ncomp` components: psi interior <- solve(rhs interior) */
+int sb200_poisson_solve(sb200_poisson_t* p, void* solution, const void* rhs, int ncomp, void* stream);
+int64_t sb200_poisson_workspace_bytes(const sb200_poisson_t* p);
+
+/* ---- immersed boundary ------------------------------------------------------
+ * numeric/immersed_boundary_ops/EulerianLagrangianGridCommunicatorMPI3D.py:116-589
+ * (+ 2D twin) and VirtualBoundaryForcingMPI.py:278-406.  Lagrangian arrays are
+ * (dim,n) device arrays of lag_dtype; substart_xyz = local interior start index
+ * in x,y,z order. */
+typedef struct sb200_ib_params {
+  int32_t lag_dtype;      /* SB200_F32 / SB200_F64 */
+  int32_t kernel_type;    /* 0 = cosine, 1 = peskin */
+  int32_t width;          /* interp_kernel_width (2) */
+  int32_t substart_xyz[3];
+  double dx;              /* value of real_t(dx) */
+  double coord_shift;     /* eul_grid_coord_shift */
+  double stiffness;       /* virtual_boundary_stiffness_coeff (already rescaled) */
+  double damping;
+} sb200_ib_params_t;
+/* steps 1-5 of compute_interaction_force_on_lag_grid (VirtualBoundaryForcingMPI.py:357-397):
+ * nearest index, weights, E->L interpolation of u, velocity mismatch, penalty force.
+ * nearest (dim,n) int64; weights ((2w)^dim, n) lag_dtype, may be NULL. */
+int sb200_ib_interact_lag(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n,
+                          const void* eul_velocity, const void* lag_position, const void* lag_velocity,
+                          const void* position_mismatch, void* nearest, void* weights,
+                          void* flow_velocity, void* velocity_mismatch, void* forcing, void* stream);
+/* L->E spreading without ghost sum: ...MPI3D.py:329-427 */
+int sb200_ib_spread(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n, void* eul_forcing,
+                    const void* lag_forcing, const void* lag_position, void* stream);
+/* zero all ghost cells: ...MPI3D.py:786-792 */
+int sb200_clear_ghost_cells(const sb200_grid_t* g, void* field, int ncomp, void* stream);
+/* dst interior-adjacent layers += src slab (ghost-sum receive side): ...MPI3D.py:689-784 */
+int sb200_ghost_sum_add_z(const sb200_grid_t* g, void* field, int ncomp, const void* from_prev,
+                          const void* from_next, void* stream);
+/* generic E->L interpolation of an n_components field (the communicator's public kernel) */
+int sb200_ib_interpolate(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n, int ncomp,
+                         const void* eul_field, const void* lag_position, void* lag_field, void* stream);
+/* position_mismatch += dt * velocity_mismatch: VirtualBoundaryForcingMPI.py:293-307 */
+int sb200_ib_update_position_mismatch(int lag_dtype, void* position_mismatch, const void* velocity_mismatch,
+                                      int64_t count, double dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOPHT_B200_H */

@@ -1,0 +1,329 @@
+// Immersed-boundary kernels: one warp per Lagrangian point, the (2w)^dim
+// support cells are spread over the lanes, shuffle-reduced.
+// Follows reference numeric/immersed_boundary_ops/EulerianLagrangianGridCommunicatorMPI3D.py
+// (:116-178 support/nearest index, :443-589 weights, :181-326 E->L, :329-427 L->E)
+// and VirtualBoundaryForcingMPI.py:278-331.
+#include "sb200_common.h"
+#include <type_traits>
+
+// numpy / numba floor division for floats (npy_divmod): exact fmod based, so
+// nearest indices are bit-identical with the reference.
+template <typename C>
+SB_D C sb_floor_divide(C a, C b) {
+  C mod = fmod(a, b);
+  C div = (a - mod) / b;
+  if (mod != C(0)) {
+    if ((b < C(0)) != (mod < C(0))) {
+      mod += b;
+      div -= C(1);
+    }
+  }
+  C floordiv;
+  if (div != C(0)) {
+    floordiv = floor(div);
+    if (div - floordiv > C(0.5)) floordiv += C(1);
+  } else {
+    floordiv = C(0);
+  }
+  return floordiv;
+}
+
+template <typename TL>
+struct SbIbP {
+  int dim, width, kernel_type;
+  long long sub_shift[3];  // substart_xyz - gs
+  double dx, shift;
+  TL weight_prefac;  // real_t((0.25/dx)**dim) or (0.125/dx)**dim
+  TL half_pi;        // real_t(0.5*pi)
+};
+
+// 1D delta-kernel factor for scaled distance r = support/dx
+template <typename TL>
+SB_D TL sb_delta_1d(const SbIbP<TL>& P, TL s_over_dx) {
+  if (P.kernel_type == 0) return TL(1) + cos(P.half_pi * s_over_dx);
+  const TL r = fabs(s_over_dx);
+  TL v = 0;
+  if (r < TL(1))
+    v = TL(3) - TL(2) * r + sqrt(fabs(TL(1) + TL(4) * r - TL(4) * r * r));
+  else if (r < TL(2))
+    v = TL(5) - TL(2) * r - sqrt(fabs(TL(-7) + TL(12) * r - TL(4) * r * r));
+  return v;
+}
+
+// nearest index (local padded frame) and scaled support offset of cell k along axis d
+template <typename TL, typename TC>
+SB_D long long sb_nearest(const SbIbP<TL>& P, TL pos, int d) {
+  const TC q = sb_floor_divide<TC>((TC)pos - (TC)P.shift, (TC)P.dx);
+  return (long long)q - P.sub_shift[d];
+}
+template <typename TL>
+SB_D TL sb_support_scaled(const SbIbP<TL>& P, long long nearest, int off, TL pos, int d) {
+  // (idx + off + sub_shift) * dx + shift - pos  evaluated in double, stored as TL, then /= dx
+  const double s = (double)(nearest + off + P.sub_shift[d]) * P.dx + P.shift - (double)pos;
+  return (TL)s / (TL)P.dx;
+}
+
+template <typename TE, typename TL, typename TC>
+__global__ void __launch_bounds__(128)
+    sb_ib_interact_kernel(SbGeom g, SbIbP<TL> P, long long n, int ncomp, const TE* eul, const TL* pos,
+                          const TL* vel, const TL* dpos, long long* nearest_out, TL* weights_out,
+                          TL* flow_vel, TL* dvel, TL* force, double dx_pow_dim, TL kcoef, TL ccoef) {
+  const unsigned lane = threadIdx.x & 31;
+  const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pt >= n) return;  // whole warp exits together
+  const int dim = P.dim, kw = 2 * P.width;
+  long long near[3] = {0, 0, 0};
+  TL p[3] = {0, 0, 0};
+  for (int d = 0; d < dim; ++d) {
+    p[d] = pos[d * n + pt];
+    near[d] = sb_nearest<TL, TC>(P, p[d], d);
+  }
+  if (nearest_out && lane == 0)
+    for (int d = 0; d < dim; ++d) nearest_out[d * n + pt] = near[d];
+  const int ncell = dim == 3 ? kw * kw * kw : kw * kw;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int cell = lane; cell < ncell; cell += 32) {
+    const int kx = cell % kw, ky = (cell / kw) % kw, kz = cell / (kw * kw);
+    const int off0 = -P.width + 1;
+    TL w = P.weight_prefac * sb_delta_1d(P, sb_support_scaled(P, near[0], kx + off0, p[0], 0));
+    w = w * sb_delta_1d(P, sb_support_scaled(P, near[1], ky + off0, p[1], 1));
+    if (dim == 3) w = w * sb_delta_1d(P, sb_support_scaled(P, near[2], kz + off0, p[2], 2));
+    if (weights_out) weights_out[(long long)cell * n + pt] = w;
+    const long long x = near[0] + kx + off0, y = near[1] + ky + off0;
+    const long long z = dim == 3 ? near[2] + kz + off0 : 0;
+    if (x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz) {
+      const long long i = (z * g.my + y) * g.mx + x;
+      for (int c = 0; c < ncomp; ++c) acc[c] += (double)eul[i + c * g.vol] * (double)w;
+    }
+  }
+  for (int c = 0; c < ncomp; ++c)
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  if (lane == 0) {
+    for (int c = 0; c < ncomp; ++c) {
+      const TL u = (TL)(acc[c] * dx_pow_dim);
+      flow_vel[c * n + pt] = u;
+      if (force) {
+        const TL dv = u - vel[c * n + pt];
+        dvel[c * n + pt] = dv;
+        force[c * n + pt] = kcoef * dpos[c * n + pt] + ccoef * dv;
+      }
+    }
+  }
+}
+
+template <typename TE, typename TL, typename TC>
+__global__ void __launch_bounds__(128)
+    sb_ib_spread_kernel(SbGeom g, SbIbP<TL> P, long long n, TE* eul, const TL* lag, const TL* pos) {
+  const unsigned lane = threadIdx.x & 31;
+  const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pt >= n) return;
+  const int dim = P.dim, kw = 2 * P.width;
+  long long near[3] = {0, 0, 0};
+  TL p[3] = {0, 0, 0}, f[3] = {0, 0, 0};
+  for (int d = 0; d < dim; ++d) {
+    p[d] = pos[d * n + pt];
+    f[d] = lag[d * n + pt];
+    near[d] = sb_nearest<TL, TC>(P, p[d], d);
+  }
+  const int ncell = dim == 3 ? kw * kw * kw : kw * kw;
+  for (int cell = lane; cell < ncell; cell += 32) {
+    const int kx = cell % kw, ky = (cell / kw) % kw, kz = cell / (kw * kw);
+    const int off0 = -P.width + 1;
+    TL w = P.weight_prefac * sb_delta_1d(P, sb_support_scaled(P, near[0], kx + off0, p[0], 0));
+    w = w * sb_delta_1d(P, sb_support_scaled(P, near[1], ky + off0, p[1], 1));
+    if (dim == 3) w = w * sb_delta_1d(P, sb_support_scaled(P, near[2], kz + off0, p[2], 2));
+    const long long x = near[0] + kx + off0, y = near[1] + ky + off0;
+    const long long z = dim == 3 ? near[2] + kz + off0 : 0;
+    if (x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz) {
+      const long long i = (z * g.my + y) * g.mx + x;
+      for (int c = 0; c < dim; ++c) atomicAdd(&eul[i + c * g.vol], (TE)(f[c] * w));
+    }
+  }
+}
+
+template <typename TL>
+static int sb_make_ib(const sb200_grid_t* gr, const sb200_ib_params_t* p, SbIbP<TL>* o) {
+  o->dim = gr->dim;
+  o->width = p->width;
+  o->kernel_type = p->kernel_type;
+  for (int d = 0; d < 3; ++d) o->sub_shift[d] = (long long)p->substart_xyz[d] - gr->gs;
+  o->dx = p->dx;
+  o->shift = p->coord_shift;
+  // constants rounded through real_t exactly as the reference does
+  // (...MPI3D.py:464-477: real_t((0.25/dx)**dim), real_t(0.5*pi))
+  const double base = (p->kernel_type == 0 ? 0.25 : 0.125) / p->dx;
+  double pref = base;
+  for (int d = 1; d < gr->dim; ++d) pref *= base;
+  if (gr->dtype == SB200_F32) {
+    o->weight_prefac = (TL)(float)pref;
+    o->half_pi = (TL)(float)(0.5 * M_PI);
+  } else {
+    o->weight_prefac = (TL)pref;
+    o->half_pi = (TL)(0.5 * M_PI);
+  }
+  return 0;
+}
+
+template <typename TE, typename TL>
+static int ib_interact_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, long long n, int ncomp,
+                         const void* eul, const void* pos, const void* vel, const void* dpos,
+                         void* nearest, void* weights, void* flow_vel, void* dvel, void* force,
+                         void* stream) {
+  // index arithmetic in the promoted type of (lag dtype, real_t)
+  using TC = typename std::conditional<(sizeof(TE) > sizeof(TL)), TE, TL>::type;
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SbIbP<TL> P;
+  sb_make_ib<TL>(gr, p, &P);
+  if (n <= 0) return 0;
+  double dxp = 1.0;
+  // reference: dx**grid_dim with dx a real_t scalar
+  if (gr->dtype == SB200_F32) {
+    float d = (float)p->dx, a = d;
+    for (int k = 1; k < gr->dim; ++k) a *= d;
+    dxp = a;
+  } else {
+    for (int k = 0; k < gr->dim; ++k) dxp *= p->dx;
+  }
+  const int warps = 4;
+  dim3 block(32 * warps), grid((unsigned)((n + warps - 1) / warps));
+  SB_LAUNCH_COOP((sb_ib_interact_kernel<TE, TL, TC>), grid, block, 0, stream, g, P, n, ncomp,
+                 (const TE*)eul, (const TL*)pos, (const TL*)vel, (const TL*)dpos, (long long*)nearest,
+                 (TL*)weights, (TL*)flow_vel, (TL*)dvel, (TL*)force, dxp, (TL)p->stiffness,
+                 (TL)p->damping);
+  SB_CHECK_LAUNCH("ib_interact");
+  return 0;
+}
+
+template <typename TE, typename TL>
+static int ib_spread_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, long long n, void* eul,
+                       const void* lag, const void* pos, void* stream) {
+  using TC = typename std::conditional<(sizeof(TE) > sizeof(TL)), TE, TL>::type;
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SbIbP<TL> P;
+  sb_make_ib<TL>(gr, p, &P);
+  if (n <= 0) return 0;
+  const int warps = 4;
+  dim3 block(32 * warps), grid((unsigned)((n + warps - 1) / warps));
+  SB_LAUNCH_COOP((sb_ib_spread_kernel<TE, TL, TC>), grid, block, 0, stream, g, P, n, (TE*)eul,
+                 (const TL*)lag, (const TL*)pos);
+  SB_CHECK_LAUNCH("ib_spread");
+  return 0;
+}
+
+#define SB_DISPATCH_2(edt, ldt, CALL)                                   \
+  do {                                                                  \
+    if ((edt) == SB200_F32 && (ldt) == SB200_F32) {                     \
+      using TE = float; using TL = float; CALL;                         \
+    } else if ((edt) == SB200_F32 && (ldt) == SB200_F64) {              \
+      using TE = float; using TL = double; CALL;                        \
+    } else if ((edt) == SB200_F64 && (ldt) == SB200_F64) {              \
+      using TE = double; using TL = double; CALL;                       \
+    } else if ((edt) == SB200_F64 && (ldt) == SB200_F32) {              \
+      using TE = double; using TL = float; CALL;                        \
+    } else {                                                            \
+      sb_set_error("unsupported dtype combination");                    \
+      return -1;                                                        \
+    }                                                                   \
+  } while (0)
+
+extern "C" int sb200_ib_interact_lag(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n,
+                                     const void* eul_velocity, const void* lag_position,
+                                     const void* lag_velocity, const void* position_mismatch,
+                                     void* nearest, void* weights, void* flow_velocity,
+                                     void* velocity_mismatch, void* forcing, void* stream) {
+  SB_REQUIRE(g && p, "ib: null params");
+  SB_REQUIRE(p->width == 2, "Interpolation kernel inconsistent with interpolation kernel width!");
+  SB_REQUIRE(g->gs >= p->width, "ghost size needs to be >= interp kernel width");
+  SB_DISPATCH_2(g->dtype, p->lag_dtype,
+                return (ib_interact_t<TE, TL>(g, p, n, g->dim, eul_velocity, lag_position, lag_velocity,
+                                              position_mismatch, nearest, weights, flow_velocity,
+                                              velocity_mismatch, forcing, stream)));
+}
+
+extern "C" int sb200_ib_interpolate(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n, int ncomp,
+                                    const void* eul_field, const void* lag_position, void* lag_field,
+                                    void* stream) {
+  SB_REQUIRE(g && p, "ib: null params");
+  SB_REQUIRE(p->width == 2, "Interpolation kernel inconsistent with interpolation kernel width!");
+  SB_REQUIRE(ncomp == 1 || ncomp == g->dim, "invalid number of components for interpolation!");
+  SB_DISPATCH_2(g->dtype, p->lag_dtype,
+                return (ib_interact_t<TE, TL>(g, p, n, ncomp, eul_field, lag_position, nullptr, nullptr,
+                                              nullptr, nullptr, lag_field, nullptr, nullptr, stream)));
+}
+
+extern "C" int sb200_ib_spread(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n,
+                               void* eul_forcing, const void* lag_forcing, const void* lag_position,
+                               void* stream) {
+  SB_REQUIRE(g && p, "ib: null params");
+  SB_REQUIRE(p->width == 2, "Interpolation kernel inconsistent with interpolation kernel width!");
+  SB_DISPATCH_2(g->dtype, p->lag_dtype,
+                return (ib_spread_t<TE, TL>(g, p, n, eul_forcing, lag_forcing, lag_position, stream)));
+}
+
+// ------------------------------------------------------------ ghost cells --
+template <typename T>
+struct ClearGhostOp {
+  T* f;
+  int ncomp;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    if (g.interior(z, y, x)) return;
+    const long long i = g.idx(z, y, x);
+    for (int c = 0; c < ncomp; ++c) f[i + c * g.vol] = 0;
+  }
+};
+extern "C" int sb200_clear_ghost_cells(const sb200_grid_t* gr, void* field, int ncomp, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_DISPATCH_DTYPE(gr->dtype,
+                    return sb_launch_cells(g, ClearGhostOp<T>{(T*)field, ncomp}, stream, "clear_ghost"));
+}
+
+// field[gs:2gs] += from_prev ; field[-2gs:-gs] += from_next   (z slabs of gs padded planes,
+// per component; either pointer may be NULL).  Reference ...MPI3D.py:689-760 for z-slab topologies.
+template <typename T>
+struct GhostSumAddOp {
+  T* f;
+  const T* prev;
+  const T* next;
+  long long n, slab;  // slab = gs*plane
+  long long vol, lo_off, hi_off;
+  SB_D void operator()(long long i) const {
+    const long long c = i / slab, r = i - c * slab;
+    if (prev) f[c * vol + lo_off + r] += prev[i];
+    if (next) f[c * vol + hi_off + r] += next[i];
+  }
+};
+extern "C" int sb200_ghost_sum_add_z(const sb200_grid_t* gr, void* field, int ncomp, const void* from_prev,
+                                     const void* from_next, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  // slab axis: z in 3D, y in 2D (leading array axis)
+  const long long line = g.dim == 3 ? g.plane : g.mx;
+  const long long lead = g.dim == 3 ? g.mz : g.my;
+  const long long slab = (long long)g.gs * line;
+  const long long count = slab * ncomp;
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_flat(
+                                   count,
+                                   GhostSumAddOp<T>{(T*)field, (const T*)from_prev, (const T*)from_next,
+                                                    count, slab, g.vol, (long long)g.gs * line,
+                                                    (lead - 2 * g.gs) * line},
+                                   stream, "ghost_sum_add"));
+}
+
+template <typename T>
+struct MismatchOp {
+  T* dx;
+  const T* dv;
+  T dt;
+  SB_D void operator()(long long i) const { dx[i] = dx[i] + dt * dv[i]; }
+};
+extern "C" int sb200_ib_update_position_mismatch(int lag_dtype, void* position_mismatch,
+                                                 const void* velocity_mismatch, int64_t count, double dt,
+                                                 void* stream) {
+  SB_DISPATCH_DTYPE(lag_dtype, return sb_launch_flat(count,
+                                                     MismatchOp<T>{(T*)position_mismatch,
+                                                                   (const T*)velocity_mismatch, (T)dt},
+                                                     stream, "ib_mismatch"));
+}

@@ -1,0 +1,203 @@
+// Interior reductions (stable-dt / diagnostics) and the fused
+// "velocity from stream function" sweep.
+#include "sb200_common.h"
+
+// order-preserving map double -> uint64 so that atomicMax works for signed values
+SB_D unsigned long long sb_key_from_double(double v) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+SB_D double sb_double_from_key(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+}
+
+// block-wide max / sum of one double per thread; result valid in thread 0
+template <bool IsMax>
+SB_D double sb_block_reduce(double v) {
+  __shared__ double sh[32];
+  const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const unsigned nthreads = blockDim.x * blockDim.y * blockDim.z;
+  const unsigned lane = tid & 31, warp = tid >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = IsMax ? (other > v ? other : v) : v + other;
+  }
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned nw = (nthreads + 31) / 32;
+    v = lane < nw ? sh[lane] : (IsMax ? -1.0e300 : 0.0);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = IsMax ? (other > v ? other : v) : v + other;
+    }
+  }
+  return v;
+}
+
+// mode 0: max of sum_c |f_c| ; 1: signed max over comps ; 2: sum of squares
+template <typename T, int MODE>
+__global__ void __launch_bounds__(512) sb_reduce_kernel(SbGeom g, const T* f, int ncomp, void* out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = blockIdx.z * blockDim.z + threadIdx.z;
+  double v = MODE == 2 ? 0.0 : -1.0e300;
+  if (x < g.mx && y < g.my && z < g.mz && g.interior(z, y, x)) {
+    const long long i = g.idx(z, y, x);
+    if (MODE == 0) {
+      T s = 0;
+      for (int c = 0; c < ncomp; ++c) s += fabs(f[i + c * g.vol]);
+      v = (double)s;
+    } else if (MODE == 1) {
+      for (int c = 0; c < ncomp; ++c) {
+        const double t = (double)f[i + c * g.vol];
+        v = t > v ? t : v;
+      }
+    } else {
+      for (int c = 0; c < ncomp; ++c) {
+        const double t = (double)f[i + c * g.vol];
+        v += t * t;
+      }
+    }
+  }
+  v = sb_block_reduce<MODE != 2>(v);
+  const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  if (tid == 0) {
+    if (MODE == 2)
+      atomicAdd((double*)out, v);
+    else
+      atomicMax((unsigned long long*)out, sb_key_from_double(v));
+  }
+}
+
+__global__ void sb_decode_key_kernel(void* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long k = *(unsigned long long*)out;
+    *(double*)out = sb_double_from_key(k);
+  }
+}
+
+template <int MODE>
+static int sb_reduce(const sb200_grid_t* gr, const void* field, int ncomp, void* out, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(out && field, "reduce: null pointer");
+  int e = sb_memset_async(out, 0, 8, stream);
+  SB_REQUIRE(e == 0, "reduce: memset failed");
+  dim3 block(64, 4, g.dim == 3 ? 2 : 1);
+  dim3 grid((g.mx + block.x - 1) / block.x, (g.my + block.y - 1) / block.y,
+            (g.mz + block.z - 1) / block.z);
+  if (gr->dtype == SB200_F32) {
+    SB_LAUNCH_COOP((sb_reduce_kernel<float, MODE>), grid, block, 0, stream, g, (const float*)field,
+                   ncomp, out);
+  } else {
+    SB_LAUNCH_COOP((sb_reduce_kernel<double, MODE>), grid, block, 0, stream, g, (const double*)field,
+                   ncomp, out);
+  }
+  SB_CHECK_LAUNCH("reduce");
+  if (MODE != 2) {
+    SB_LAUNCH(sb_decode_key_kernel, dim3(1), dim3(32), 0, stream, out);
+    SB_CHECK_LAUNCH("reduce_decode");
+  }
+  return 0;
+}
+
+extern "C" int sb200_max_abs_sum(const sb200_grid_t* g, const void* f, int ncomp, void* out, void* stream) {
+  return sb_reduce<0>(g, f, ncomp, out, stream);
+}
+extern "C" int sb200_max(const sb200_grid_t* g, const void* f, int ncomp, void* out, void* stream) {
+  return sb_reduce<1>(g, f, ncomp, out, stream);
+}
+extern "C" int sb200_sum_squares(const sb200_grid_t* g, const void* f, int ncomp, void* out, void* stream) {
+  return sb_reduce<2>(g, f, ncomp, out, stream);
+}
+
+// --------------------------------------------------------------------------
+// u = p*curl(psi) on the wrapper's cells, 0 on the physical ring, + U_inf;
+// F = 0; max over interior of sum_c |u_c|  -- one read of psi, one write of u.
+// (reference flow_simulators_mpi_3d.py:388-393, 422-424, 429-442)
+template <typename T>
+__global__ void __launch_bounds__(512)
+    sb_velocity_kernel(SbGeom g, T* u, const T* psi, T p, T u0, T u1, T u2, T* forcing, void* max_out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = blockIdx.z * blockDim.z + threadIdx.z;
+  double v = -1.0e300;
+  if (x < g.mx && y < g.my && z < g.mz) {
+    const long long i = g.idx(z, y, x);
+    const bool ring = g.in_ring(z, y, x);
+    const bool wr = g.written(z, y, x, 1, g.dim == 3);
+    const int nc = g.dim;
+    T c[3] = {0, 0, 0};
+    if (ring || wr) {
+      if (!ring) {
+        if (g.dim == 3) {
+          const long long n = g.vol, sy = g.mx, sz = g.plane;
+          const T* fx = psi;
+          const T* fy = psi + n;
+          const T* fz = psi + 2 * n;
+          c[0] = p * (fz[i + sy] - fz[i - sy] - fy[i + sz] + fy[i - sz]);
+          c[1] = p * (fx[i + sz] - fx[i - sz] - fz[i + 1] + fz[i - 1]);
+          c[2] = p * (fy[i + 1] - fy[i - 1] - fx[i + sy] + fx[i - sy]);
+        } else {
+          c[0] = p * (psi[i + g.mx] - psi[i - g.mx]);
+          c[1] = -p * (psi[i + 1] - psi[i - 1]);
+        }
+      }
+    } else {
+      for (int k = 0; k < nc; ++k) c[k] = u[i + k * g.vol];
+    }
+    c[0] += u0;
+    c[1] += u1;
+    c[2] += u2;
+    T s = 0;
+    for (int k = 0; k < nc; ++k) {
+      u[i + k * g.vol] = c[k];
+      s += fabs(c[k]);
+      if (forcing) forcing[i + k * g.vol] = 0;
+    }
+    if (g.interior(z, y, x)) v = (double)s;
+  }
+  if (max_out) {
+    v = sb_block_reduce<true>(v);
+    const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    if (tid == 0) atomicMax((unsigned long long*)max_out, sb_key_from_double(v));
+  }
+}
+
+extern "C" int sb200_velocity_from_stream_function(const sb200_grid_t* gr, void* velocity,
+                                                   const void* stream_func, double prefactor,
+                                                   const double* free_stream, void* forcing, void* max_out,
+                                                   void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  double fs[3] = {0, 0, 0};
+  if (free_stream)
+    for (int k = 0; k < g.dim; ++k) fs[k] = free_stream[k];
+  if (max_out) {
+    int e = sb_memset_async(max_out, 0, 8, stream);
+    SB_REQUIRE(e == 0, "velocity: memset failed");
+  }
+  dim3 block(64, 4, g.dim == 3 ? 2 : 1);
+  dim3 grid((g.mx + block.x - 1) / block.x, (g.my + block.y - 1) / block.y,
+            (g.mz + block.z - 1) / block.z);
+  if (gr->dtype == SB200_F32) {
+    SB_LAUNCH_COOP(sb_velocity_kernel<float>, grid, block, 0, stream, g, (float*)velocity,
+                   (const float*)stream_func, (float)prefactor, (float)fs[0], (float)fs[1], (float)fs[2],
+                   (float*)forcing, max_out);
+  } else {
+    SB_LAUNCH_COOP(sb_velocity_kernel<double>, grid, block, 0, stream, g, (double*)velocity,
+                   (const double*)stream_func, prefactor, fs[0], fs[1], fs[2], (double*)forcing, max_out);
+  }
+  SB_CHECK_LAUNCH("velocity_from_stream_function");
+  if (max_out) {
+    SB_LAUNCH(sb_decode_key_kernel, dim3(1), dim3(32), 0, stream, max_out);
+    SB_CHECK_LAUNCH("velocity_decode");
+  }
+  return 0;
+}

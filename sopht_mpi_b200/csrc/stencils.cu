@@ -1,0 +1,477 @@
+// Eulerian grid operators (one launch per reference operator).
+// Each operator reproduces the cells the reference MPI wrapper writes:
+// interior + six boundary slabs + zeroed physical ring (SbGeom::written/in_ring).
+#include "sb200_common.h"
+
+#include <cstdarg>
+
+static thread_local char g_err[512] = "";
+void sb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* sb200_last_error(void) { return g_err; }
+extern "C" int sb200_version(void) { return 100; }
+
+// ------------------------------------------------------------ pointwise ----
+template <typename T>
+struct FillOp {
+  T* f;
+  T v;
+  SB_D void operator()(long long i) const { f[i] = v; }
+};
+template <typename T>
+struct SumOp {
+  T* s;
+  const T* a;
+  const T* b;
+  SB_D void operator()(long long i) const { s[i] = a[i] + b[i]; }
+};
+template <typename T>
+struct CopyOp {
+  T* d;
+  const T* s;
+  SB_D void operator()(long long i) const { d[i] = s[i]; }
+};
+template <typename T>
+struct SaxpbyOp {
+  T* s;
+  const T* a;
+  const T* b;
+  T pa, pb;
+  SB_D void operator()(long long i) const { s[i] = pa * a[i] + pb * b[i]; }
+};
+template <typename T>
+struct CrossOp {
+  T* r;
+  const T* a;
+  const T* b;
+  long long n;
+  SB_D void operator()(long long i) const {
+    const T a0 = a[i], a1 = a[i + n], a2 = a[i + 2 * n];
+    const T b0 = b[i], b1 = b[i + n], b2 = b[i + 2 * n];
+    r[i] = a1 * b2 - a2 * b1;
+    r[i + n] = a2 * b0 - a0 * b2;
+    r[i + 2 * n] = a0 * b1 - a1 * b0;
+  }
+};
+template <typename T>
+struct AddFixedOp {
+  T* f;
+  long long n;
+  int ncomp;
+  T v0, v1, v2;
+  SB_D void operator()(long long i) const {
+    f[i] += v0;
+    if (ncomp > 1) f[i + n] += v1;
+    if (ncomp > 2) f[i + 2 * n] += v2;
+  }
+};
+
+extern "C" int sb200_set_fixed_val(int dtype, void* field, int64_t count, double value, void* stream) {
+  SB_REQUIRE(field || count == 0, "set_fixed_val: null field");
+  if (value == 0.0) {
+    size_t w = dtype == SB200_F32 ? 4 : 8;
+    int e = sb_memset_async(field, 0, (size_t)count * w, stream);
+    if (e) {
+      sb_set_error("memset: %s", sb_error_string(e));
+      return -2;
+    }
+    return 0;
+  }
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(count, FillOp<T>{(T*)field, (T)value}, stream, "fill"));
+}
+extern "C" int sb200_elementwise_sum(int dtype, void* sum, const void* a, const void* b, int64_t count,
+                                     void* stream) {
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(count, SumOp<T>{(T*)sum, (const T*)a, (const T*)b},
+                                                 stream, "sum"));
+}
+extern "C" int sb200_elementwise_copy(int dtype, void* dst, const void* src, int64_t count, void* stream) {
+  SB_DISPATCH_DTYPE(dtype,
+                    return sb_launch_flat(count, CopyOp<T>{(T*)dst, (const T*)src}, stream, "copy"));
+}
+extern "C" int sb200_elementwise_saxpby(int dtype, void* sum, const void* a, double pa, const void* b,
+                                        double pb, int64_t count, void* stream) {
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(
+                               count, SaxpbyOp<T>{(T*)sum, (const T*)a, (const T*)b, (T)pa, (T)pb},
+                               stream, "saxpby"));
+}
+extern "C" int sb200_elementwise_cross_product(int dtype, void* result, const void* f1, const void* f2,
+                                               int64_t count, void* stream) {
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(
+                               count, CrossOp<T>{(T*)result, (const T*)f1, (const T*)f2, count}, stream,
+                               "cross"));
+}
+extern "C" int sb200_add_fixed_val(int dtype, void* field, int ncomp, int64_t count, const double* vals,
+                                   void* stream) {
+  SB_REQUIRE(ncomp >= 1 && ncomp <= 3 && vals, "add_fixed_val: bad ncomp/vals");
+  double v[3] = {vals[0], ncomp > 1 ? vals[1] : 0.0, ncomp > 2 ? vals[2] : 0.0};
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(
+                               count, AddFixedOp<T>{(T*)field, count, ncomp, (T)v[0], (T)v[1], (T)v[2]},
+                               stream, "add_fixed"));
+}
+
+// -------------------------------------------------------------- stencils ---
+// curl components of a (3,z,y,x) field at linear index i (unit prefactor applied by caller)
+template <typename T>
+SB_D void curl3_at(const SbGeom& g, const T* f, long long i, T p, T& cx, T& cy, T& cz) {
+  const long long n = g.vol, sy = g.mx, sz = g.plane;
+  const T* fx = f;
+  const T* fy = f + n;
+  const T* fz = f + 2 * n;
+  cx = p * (fz[i + sy] - fz[i - sy] - fy[i + sz] + fy[i - sz]);
+  cy = p * (fx[i + sz] - fx[i - sz] - fz[i + 1] + fz[i - 1]);
+  cz = p * (fy[i + 1] - fy[i - 1] - fx[i + sy] + fx[i - sy]);
+}
+
+template <typename T>
+struct UpdateVorticityOp {
+  T* w;
+  const T* f;
+  T p;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    if (!g.written(z, y, x, 1)) return;
+    const long long i = g.idx(z, y, x);
+    if (g.dim == 3) {
+      T cx, cy, cz;
+      curl3_at(g, f, i, p, cx, cy, cz);
+      w[i] += cx;
+      w[i + g.vol] += cy;
+      w[i + 2 * g.vol] += cz;
+    } else {
+      // omega += p * (dFy/dx - dFx/dy), F is (2,y,x)
+      const T* fx = f;
+      const T* fy = f + g.vol;
+      w[i] += p * (fy[i + 1] - fy[i - 1] - fx[i + g.mx] + fx[i - g.mx]);
+    }
+  }
+};
+
+template <typename T>
+struct CurlOp {
+  T* c;
+  const T* f;
+  T p;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    const long long i = g.idx(z, y, x);
+    const bool ring = g.in_ring(z, y, x);
+    const bool wr = g.written(z, y, x, 1, /*x_full=*/g.dim == 3);
+    if (!ring && !wr) return;
+    if (g.dim == 3) {
+      T cx = 0, cy = 0, cz = 0;
+      if (!ring) curl3_at(g, f, i, p, cx, cy, cz);
+      c[i] = cx;
+      c[i + g.vol] = cy;
+      c[i + 2 * g.vol] = cz;
+    } else {
+      // outplane curl: psi (y,x) -> (u_x, u_y) = p * (dpsi/dy, -dpsi/dx)
+      T ux = 0, uy = 0;
+      if (!ring) {
+        ux = p * (f[i + g.mx] - f[i - g.mx]);
+        uy = -p * (f[i + 1] - f[i - 1]);
+      }
+      c[i] = ux;
+      c[i + g.vol] = uy;
+    }
+  }
+};
+
+template <typename T>
+struct DiffusionFluxOp {
+  T* flux;
+  const T* f;
+  T p;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    const long long i = g.idx(z, y, x);
+    if (g.in_ring(z, y, x)) {
+      flux[i] = 0;
+      return;
+    }
+    if (!g.written(z, y, x, 1)) return;
+    T s = f[i + 1] + f[i - 1] + f[i + g.mx] + f[i - g.mx];
+    if (g.dim == 3) {
+      s += f[i + g.plane] + f[i - g.plane];
+      flux[i] = p * (s - T(6) * f[i]);
+    } else {
+      flux[i] = p * (s - T(4) * f[i]);
+    }
+  }
+};
+
+template <typename T>
+struct DivergenceOp {
+  T* d;
+  const T* f;
+  T p;  // 0.5 * inv_dx
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    const long long i = g.idx(z, y, x);
+    if (g.in_ring(z, y, x)) {
+      d[i] = 0;
+      return;
+    }
+    if (!g.written(z, y, x, 1)) return;
+    const T* fx = f;
+    const T* fy = f + g.vol;
+    T s = fx[i + 1] - fx[i - 1] + fy[i + g.mx] - fy[i - g.mx];
+    if (g.dim == 3) {
+      const T* fz = f + 2 * g.vol;
+      s += fz[i + g.plane] - fz[i - g.plane];
+    }
+    d[i] = p * s;
+  }
+};
+
+// ENO3 upwinded flux difference along one axis (stride st) for cell i
+template <typename T>
+SB_D T eno3_axis(const T* q, const T* v, long long i, long long st) {
+  const T half = T(0.5), sixth = T(1.0 / 6.0);
+  const T qm2 = q[i - 2 * st], qm1 = q[i - st], q0 = q[i], qp1 = q[i + st], qp2 = q[i + 2 * st];
+  const T vp = half * (v[i] + v[i + st]);
+  const T vm = half * (v[i] + v[i - st]);
+  const T fl_p = sixth * (-qm1 + T(5) * q0 + T(2) * qp1);
+  const T fr_p = sixth * (T(2) * q0 + T(5) * qp1 - qp2);
+  const T fl_m = sixth * (-qm2 + T(5) * qm1 + T(2) * q0);
+  const T fr_m = sixth * (T(2) * qm1 + T(5) * q0 - qp1);
+  const T zero = T(0);
+  const T flux_p = (vp > zero ? vp : zero) * fl_p + (vp < zero ? vp : zero) * fr_p;
+  const T flux_m = (vm > zero ? vm : zero) * fl_m + (vm < zero ? vm : zero) * fr_m;
+  return flux_p - flux_m;
+}
+
+template <typename T>
+struct AdvectionFluxOp {
+  T* flux;
+  const T* q;
+  const T* vel;
+  T inv_dx;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    if (!g.written(z, y, x, 2)) return;
+    const long long i = g.idx(z, y, x);
+    T s = eno3_axis(q, vel, i, 1) + eno3_axis(q, vel + g.vol, i, (long long)g.mx);
+    if (g.dim == 3) s += eno3_axis(q, vel + 2 * g.vol, i, g.plane);
+    flux[i] = inv_dx * s;
+  }
+};
+
+template <typename T>
+struct FilterAxisOp {
+  T* flux;
+  const T* f;
+  long long st;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    const long long i = g.idx(z, y, x);
+    // the wrapper clears the ring right after the seven calls
+    if (g.in_ring(z, y, x)) {
+      flux[i] = 0;
+      return;
+    }
+    if (!g.written(z, y, x, 1)) return;
+    flux[i] = T(0.25) * (-f[i + st] - f[i - st] + T(2) * f[i]);
+  }
+};
+
+template <typename T>
+struct ClearRingOp {
+  T* f;
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    if (g.in_ring(z, y, x)) f[g.idx(z, y, x)] = 0;
+  }
+};
+
+extern "C" int sb200_update_vorticity_from_velocity_forcing(const sb200_grid_t* gr, void* vorticity,
+                                                            const void* forcing, double prefactor,
+                                                            void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_DISPATCH_DTYPE(gr->dtype,
+                    return sb_launch_cells(g, UpdateVorticityOp<T>{(T*)vorticity, (const T*)forcing,
+                                                                   (T)prefactor},
+                                           stream, "update_vorticity"));
+}
+extern "C" int sb200_curl(const sb200_grid_t* gr, void* curl, const void* field, double prefactor,
+                          void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(
+                                   g, CurlOp<T>{(T*)curl, (const T*)field, (T)prefactor}, stream, "curl"));
+}
+extern "C" int sb200_diffusion_flux(const sb200_grid_t* gr, void* flux, const void* field, double prefactor,
+                                    void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_DISPATCH_DTYPE(gr->dtype,
+                    return sb_launch_cells(g, DiffusionFluxOp<T>{(T*)flux, (const T*)field, (T)prefactor},
+                                           stream, "diffusion_flux"));
+}
+extern "C" int sb200_diffusion_timestep(const sb200_grid_t* gr, void* field, int ncomp, void* flux,
+                                        double nu_dt_by_dx2, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  const size_t w = gr->dtype == SB200_F32 ? 4 : 8;
+  for (int c = 0; c < ncomp; ++c) {
+    char* fc = (char*)field + (size_t)c * g.vol * w;
+    int e = sb200_diffusion_flux(gr, flux, fc, nu_dt_by_dx2, stream);
+    if (e) return e;
+    e = sb200_elementwise_sum(gr->dtype, fc, fc, flux, g.vol, stream);
+    if (e) return e;
+  }
+  return 0;
+}
+extern "C" int sb200_advection_flux_eno3(const sb200_grid_t* gr, void* flux, const void* field,
+                                         const void* velocity, double inv_dx, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 2, "ghost_size < kernel_support");
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(g,
+                                                      AdvectionFluxOp<T>{(T*)flux, (const T*)field,
+                                                                         (const T*)velocity, (T)inv_dx},
+                                                      stream, "advection_flux"));
+}
+extern "C" int sb200_advection_timestep_eno3(const sb200_grid_t* gr, void* field, int ncomp, void* flux,
+                                             const void* velocity, double dt_by_dx, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  const size_t w = gr->dtype == SB200_F32 ? 4 : 8;
+  for (int c = 0; c < ncomp; ++c) {
+    char* fc = (char*)field + (size_t)c * g.vol * w;
+    int e = sb200_set_fixed_val(gr->dtype, flux, g.vol, 0.0, stream);
+    if (e) return e;
+    e = sb200_advection_flux_eno3(gr, flux, fc, velocity, -dt_by_dx, stream);
+    if (e) return e;
+    e = sb200_elementwise_sum(gr->dtype, fc, fc, flux, g.vol, stream);
+    if (e) return e;
+  }
+  return 0;
+}
+extern "C" int sb200_divergence(const sb200_grid_t* gr, void* divergence, const void* field, double inv_dx,
+                                void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(g,
+                                                      DivergenceOp<T>{(T*)divergence, (const T*)field,
+                                                                      (T)(0.5 * inv_dx)},
+                                                      stream, "divergence"));
+}
+
+template <typename T>
+static int laplacian_filter_scalar(const sb200_grid_t* gr, const SbGeom& g, T* field, int order, int type,
+                                   T* flux, T* buf, void* stream) {
+  int e;
+  // array strides of the x, y, z filters
+  const long long strides[3] = {1, (long long)g.mx, g.plane};
+  const int naxes = g.dim;
+  if ((e = sb_launch_cells(g, ClearRingOp<T>{flux}, stream, "filter_clear"))) return e;
+  if (type == 0) {
+    if ((e = sb200_elementwise_copy(gr->dtype, buf, field, g.vol, stream))) return e;
+    for (int it = 0; it < order; ++it)
+      for (int a = 0; a < naxes; ++a) {
+        if ((e = sb_launch_cells(g, FilterAxisOp<T>{flux, buf, strides[a]}, stream, "filter_axis")))
+          return e;
+        if ((e = sb200_elementwise_copy(gr->dtype, buf, flux, g.vol, stream))) return e;
+      }
+    return sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream);
+  }
+  for (int a = 0; a < naxes; ++a) {
+    if ((e = sb200_elementwise_copy(gr->dtype, buf, field, g.vol, stream))) return e;
+    for (int it = 0; it < order; ++it) {
+      if ((e = sb_launch_cells(g, FilterAxisOp<T>{flux, buf, strides[a]}, stream, "filter_axis")))
+        return e;
+      if ((e = sb200_elementwise_copy(gr->dtype, buf, flux, g.vol, stream))) return e;
+    }
+    if ((e = sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream))) return e;
+  }
+  return 0;
+}
+
+extern "C" int sb200_laplacian_filter(const sb200_grid_t* gr, void* field, int ncomp, int filter_order,
+                                      int filter_type, void* flux, void* buf, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_REQUIRE(filter_order >= 0 && (filter_type == 0 || filter_type == 1), "invalid filter setting");
+  for (int c = 0; c < ncomp; ++c) {
+    int e = 0;
+    SB_DISPATCH_DTYPE(gr->dtype, e = laplacian_filter_scalar<T>(gr, g, (T*)field + (size_t)c * g.vol,
+                                                                 filter_order, filter_type, (T*)flux,
+                                                                 (T*)buf, stream));
+    if (e) return e;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------- penalise ----
+// Sequential reference semantics (X front/back, then Y, then Z; copy the plane
+// gs+w-1 outwards, then multiply by the sine factor) collapse to
+//   f[z,y,x] = ((f[cz,cy,cx] * sx) * sy) * sz
+// with c* = index clamped into [gs+w-1, m-gs-w] along physical axes.
+// Phase 0 writes every zone cell that is not itself a source cell; phase 1 then
+// scales the source cells lying on the clamp planes.
+template <typename T>
+struct PenaliseOp {
+  T* f;
+  const T* fac;  // [2*dim][gs+w], order z_front,z_back,y_front,y_back,x_front,x_back (2D: y.., x..)
+  int w;         // gs + width
+  int phase;
+  // returns true when index i lies in a physical penalty slab of this axis
+  SB_D bool axis(int i, int m, int pf, int pb, int tab, int& ci, T& s, bool& moved) const {
+    ci = i;
+    s = T(1);
+    if (pf && i < w) {
+      ci = w - 1;
+      s = fac[tab * w + i];
+      moved = moved || (i != w - 1);
+      return true;
+    }
+    if (pb && i >= m - w) {
+      ci = m - w;
+      s = fac[(tab + 1) * w + (i - (m - w))];
+      moved = moved || (i != m - w);
+      return true;
+    }
+    return false;
+  }
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    int cz = z, cy, cx;
+    T sz = T(1), sy, sx;
+    bool moved = false;
+    const int t0 = g.dim == 3 ? 2 : 0;
+    const bool inx = axis(x, g.mx, g.phys[4], g.phys[5], t0 + 2, cx, sx, moved);
+    const bool iny = axis(y, g.my, g.phys[2], g.phys[3], t0, cy, sy, moved);
+    bool inz = false;
+    if (g.dim == 3) inz = axis(z, g.mz, g.phys[0], g.phys[1], 0, cz, sz, moved);
+    if (!(inx || iny || inz)) return;
+    if ((phase == 0) != moved) return;
+    T v = f[g.idx(cz, cy, cx)];
+    // multiply by the factors of the slabs this cell belongs to, in X,Y,Z order
+    if (inx) v = v * sx;
+    if (iny) v = v * sy;
+    if (inz) v = v * sz;
+    f[g.idx(z, y, x)] = v;
+  }
+};
+
+extern "C" int sb200_penalise_field_boundary(const sb200_grid_t* gr, void* field, int ncomp, int width,
+                                             const void* factors, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(width >= 0, "invalid zone width");
+  if (width == 0) return 0;
+  const int w = g.gs + width;
+  SB_REQUIRE(g.mx >= 2 * w && g.my >= 2 * w && (g.dim == 2 || g.mz >= 2 * w), "penalty zones overlap");
+  for (int c = 0; c < ncomp; ++c)
+    for (int phase = 0; phase < 2; ++phase) {
+      int e = 0;
+      SB_DISPATCH_DTYPE(gr->dtype, e = sb_launch_cells(g,
+                                                       PenaliseOp<T>{(T*)field + (size_t)c * g.vol,
+                                                                     (const T*)factors, w, phase},
+                                                       stream, "penalise"));
+      if (e) return e;
+    }
+  return 0;
+}
