@@ -82,6 +82,13 @@ int sb200_divergence(const sb200_grid_t* g, void* divergence, const void* field,
 /* stencil_ops_3d/laplacian_filter_mpi_3d.py:267-419; filter_type 0 = multiplicative, 1 = convolution */
 int sb200_laplacian_filter(const sb200_grid_t* g, void* field, int ncomp, int filter_order, int filter_type,
                            void* filter_flux_buffer, void* field_buffer, void* stream);
+/* one axis pass of the filter incl. the ring clearing that follows it
+ * (laplacian_filter_mpi_3d.py:145-264,118-143); axis = ARRAY axis counted from the
+ * last one: 0 = x, 1 = y, 2 = z.  Lets the host exchange halos between passes. */
+int sb200_laplacian_filter_axis(const sb200_grid_t* g, void* filter_flux, const void* field_buffer,
+                                int axis, void* stream);
+/* zero the physical-boundary ring of width gs+width (laplacian_filter_mpi_3d.py:118-143) */
+int sb200_clear_physical_ring(const sb200_grid_t* g, void* field, int ncomp, int width, void* stream);
 /* stencil_ops_3d/penalise_field_boundary_mpi_3d.py:185-267.  `factors` is a
  * DEVICE array [2*dim][gs+width] of the sine factors in real_t, ordered
  * (3D) z_front,z_back,y_front,y_back,x_front,x_back, each indexed by the

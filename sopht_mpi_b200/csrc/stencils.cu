@@ -275,8 +275,11 @@ struct FilterAxisOp {
 template <typename T>
 struct ClearRingOp {
   T* f;
+  int ncomp = 1, width = 1;
   SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
-    if (g.in_ring(z, y, x)) f[g.idx(z, y, x)] = 0;
+    if (!g.in_ring(z, y, x, width)) return;
+    const long long i = g.idx(z, y, x);
+    for (int c = 0; c < ncomp; ++c) f[i + c * g.vol] = 0;
   }
 };
 
@@ -387,6 +390,25 @@ static int laplacian_filter_scalar(const sb200_grid_t* gr, const SbGeom& g, T* f
     if ((e = sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream))) return e;
   }
   return 0;
+}
+
+extern "C" int sb200_laplacian_filter_axis(const sb200_grid_t* gr, void* flux, const void* buf, int axis,
+                                           void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_REQUIRE(axis >= 0 && axis < g.dim, "bad filter axis");
+  const long long strides[3] = {1, (long long)g.mx, g.plane};
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(
+                                   g, FilterAxisOp<T>{(T*)flux, (const T*)buf, strides[axis]}, stream,
+                                   "filter_axis"));
+}
+extern "C" int sb200_clear_physical_ring(const sb200_grid_t* gr, void* field, int ncomp, int width,
+                                         void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(g, ClearRingOp<T>{(T*)field, ncomp, width}, stream,
+                                                      "clear_ring"));
 }
 
 extern "C" int sb200_laplacian_filter(const sb200_grid_t* gr, void* field, int ncomp, int filter_order,

@@ -1,0 +1,90 @@
+"""Unbounded Poisson solvers with the reference's class names and methods
+(``sopht_mpi/numeric/eulerian_grid_ops/poisson_solver_3d/UnboundedPoissonSolverMPI3D.py:14-187``,
+``poisson_solver_2d/UnboundedPoissonSolverMPI2D.py:12-153``)."""
+import ctypes
+
+import numpy as np
+
+from ... import _lib
+from ...utils.device import Staged, current_stream_ptr, dptr
+
+
+def _is_pow2(n):
+    return n > 0 and (n & (n - 1)) == 0
+
+
+class _UnboundedPoissonSolver:
+    def __init__(self, dim, grid_size, mpi_construct, ghost_size, x_range, real_t, backend):
+        self.lib = _lib.load()
+        self.dim = dim
+        self.mpi_construct = mpi_construct
+        self.ghost_size = ghost_size
+        self.x_range = x_range
+        self.real_t = real_t
+        gs3 = [1] * (3 - dim) + [int(g) for g in grid_size]
+        self.grid_size_z, self.grid_size_y, self.grid_size_x = gs3
+        self.y_range = x_range * (self.grid_size_y / self.grid_size_x)
+        if dim == 3:
+            self.z_range = x_range * (self.grid_size_z / self.grid_size_x)
+        self.dx = real_t(x_range / self.grid_size_x)
+        self.device = mpi_construct.device
+        if self.device.type != "cuda":
+            raise _lib.SophtB200Error("the Poisson solver needs a CUDA device (no CPU fallback)")
+        if backend == "auto":
+            pow2 = all(_is_pow2(int(g)) for g in grid_size)
+            backend = "fft" if (pow2 and dim == 3 and _fft_backend_available(self.lib)) else "cufft"
+        self.backend = backend
+        self._handle = ctypes.c_void_p()
+        _lib.check(self.lib, self.lib.sb200_poisson_create(
+            ctypes.byref(self._handle), dim, _lib.dtype_code(real_t), gs3[0], gs3[1], gs3[2],
+            ghost_size, float(x_range), mpi_construct.rank, mpi_construct.size,
+            1 if backend == "fft" else 0, current_stream_ptr(self.device)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self.lib.sb200_poisson_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.sb200_poisson_workspace_bytes(self._handle))
+
+    def _solve(self, solution, rhs, ncomp):
+        st = Staged(self.device)
+        s, r = st(solution, out=True), st(rhs)
+        _lib.check(self.lib, self.lib.sb200_poisson_solve(self._handle, dptr(s), dptr(r), ncomp,
+                                                          current_stream_ptr(self.device)))
+        st.finish()
+
+    def solve(self, solution_field, rhs_field):
+        """-del^2(solution_field) = rhs_field on the unbounded domain; padded local
+        fields, only interiors are read / written."""
+        self._solve(solution_field, rhs_field, 1)
+
+
+_FFT_AVAILABLE = None
+
+
+def _fft_backend_available(lib):
+    return bool(getattr(lib, "sb200_poisson_fft_available", lambda: 0)())
+
+
+class UnboundedPoissonSolverMPI3D(_UnboundedPoissonSolver):
+    def __init__(self, grid_size_z, grid_size_y, grid_size_x, mpi_construct, ghost_size,
+                 x_range=1.0, real_t=np.float64, backend="auto"):
+        super().__init__(3, (grid_size_z, grid_size_y, grid_size_x), mpi_construct, ghost_size,
+                         x_range, real_t, backend)
+
+    def vector_field_solve(self, solution_vector_field, rhs_vector_field):
+        """three component solves (reference :169-187), batched in one call"""
+        self._solve(solution_vector_field, rhs_vector_field, 3)
+
+
+class UnboundedPoissonSolverMPI2D(_UnboundedPoissonSolver):
+    def __init__(self, grid_size_y, grid_size_x, mpi_construct, ghost_size, x_range=1.0,
+                 real_t=np.float64, backend="auto"):
+        super().__init__(2, (grid_size_y, grid_size_x), mpi_construct, ghost_size, x_range, real_t,
+                         backend)

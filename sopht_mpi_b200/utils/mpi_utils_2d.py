@@ -1,0 +1,24 @@
+"""2D topology / halo / field / Lagrangian communicators with the reference's class
+names (``sopht_mpi/utils/mpi_utils_2d.py``)."""
+import numpy as np
+
+from .comm import (MPIConstruct, MPIFieldCommunicator, MPIGhostCommunicator,
+                   MPILagrangianFieldCommunicator)
+
+
+class MPIConstruct2D(MPIConstruct):
+    def __init__(self, grid_size_y, grid_size_x, periodic_domain=False, real_t=np.float64,
+                 rank_distribution=None):
+        super().__init__(2, (grid_size_y, grid_size_x), periodic_domain, real_t, rank_distribution)
+
+
+class MPIGhostCommunicator2D(MPIGhostCommunicator):
+    pass
+
+
+class MPIFieldCommunicator2D(MPIFieldCommunicator):
+    pass
+
+
+class MPILagrangianFieldCommunicator2D(MPILagrangianFieldCommunicator):
+    pass

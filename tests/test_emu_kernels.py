@@ -1,0 +1,227 @@
+"""Kernel LOGIC check in the GPU-less container: the CUDA sources compiled with
+-DSB200_EMU (host-thread emulation, tests/emu) against the oracle.  This exercises
+the same device code the GPU runs (write masks, ring zeroing, penalise gather,
+warp-per-point IB kernels); the real parity tests are the `-m gpu` ones."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from emu_util import call, ptr
+from oracle import stencils as st
+from sopht_mpi_b200 import _lib
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _tol(real_t):
+    return 1e-13 if real_t == np.float64 else 2e-6
+
+
+@pytest.fixture(params=[np.float64, np.float32], ids=["f64", "f32"])
+def setup3d(request):
+    real_t = request.param
+    rng = np.random.default_rng(0)
+    n, gs = (9, 11, 13), 2
+    shape = tuple(v + 2 * gs for v in n)
+    g = _lib.make_grid(3, real_t, gs, n, [1] * 6)
+    return real_t, rng, n, gs, shape, g
+
+
+def test_update_vorticity_and_curl(setup3d):
+    real_t, rng, n, gs, shape, g = setup3d
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    f = rng.uniform(size=(3,) + shape).astype(real_t)
+    w0, w1 = w.copy(), w.copy()
+    st.update_vorticity_from_velocity_forcing_mpi(w0, f, 0.37, gs)
+    call("sb200_update_vorticity_from_velocity_forcing", ctypes.byref(g), ptr(w1), ptr(f), 0.37, None)
+    assert _rel(w1, w0) < _tol(real_t)
+    c0 = rng.uniform(size=(3,) + shape).astype(real_t)
+    c1 = c0.copy()
+    st.curl_mpi(c0, f, 0.8, gs)
+    call("sb200_curl", ctypes.byref(g), ptr(c1), ptr(f), 0.8, None)
+    assert _rel(c1, c0) < _tol(real_t)
+
+
+def test_partial_physical_faces_match_virtual_rank_semantics(setup3d):
+    """z faces NOT physical (inner slab of a z-slab decomposition): no z ring, no z penalty."""
+    real_t, rng, n, gs, shape, _ = setup3d
+    phys = (False, False, True, True, True, True)
+    g = _lib.make_grid(3, real_t, gs, n, phys)
+    f = rng.uniform(size=shape).astype(real_t)
+    fl0 = rng.uniform(size=shape).astype(real_t)
+    fl1 = fl0.copy()
+    st.diffusion_flux_mpi(fl0, f, 0.1, gs, phys)
+    call("sb200_diffusion_flux", ctypes.byref(g), ptr(fl1), ptr(f), 0.1, None)
+    assert _rel(fl1, fl0) < _tol(real_t)
+
+
+def test_diffusion_advection_divergence(setup3d):
+    real_t, rng, n, gs, shape, g = setup3d
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    vel = (rng.uniform(size=(3,) + shape) - 0.5).astype(real_t)
+    a0, a1 = w.copy(), w.copy()
+    b0 = rng.uniform(size=shape).astype(real_t)
+    b1 = b0.copy()
+    st.diffusion_timestep_mpi(a0, b0, 0.1, gs)
+    call("sb200_diffusion_timestep", ctypes.byref(g), ptr(a1), 3, ptr(b1), 0.1, None)
+    assert _rel(a1, a0) < _tol(real_t) and _rel(b1, b0) < _tol(real_t)
+    a0, a1 = w.copy(), w.copy()
+    b0 = np.ones(shape, real_t)
+    b1 = b0.copy()
+    st.advection_timestep_mpi(a0, b0, vel, 0.2, gs)
+    call("sb200_advection_timestep_eno3", ctypes.byref(g), ptr(a1), 3, ptr(b1), ptr(vel), 0.2, None)
+    assert _rel(a1, a0) < _tol(real_t) and _rel(b1, b0) < 10 * _tol(real_t)
+    d0 = rng.uniform(size=shape).astype(real_t)
+    d1 = d0.copy()
+    st.divergence_mpi(d0, w, 3.0, gs)
+    call("sb200_divergence", ctypes.byref(g), ptr(d1), ptr(w), 3.0, None)
+    assert _rel(d1, d0) < _tol(real_t)
+
+
+@pytest.mark.parametrize("ftype,fname", [(0, "multiplicative"), (1, "convolution")])
+def test_laplacian_filter(setup3d, ftype, fname):
+    real_t, rng, n, gs, shape, g = setup3d
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    a0, a1 = w.copy(), w.copy()
+    fb0 = rng.uniform(size=shape).astype(real_t)
+    fb1 = fb0.copy()
+    bb0, bb1 = np.zeros(shape, real_t), np.zeros(shape, real_t)
+    st.laplacian_filter_mpi(a0, fb0, bb0, 2, fname, gs)
+    call("sb200_laplacian_filter", ctypes.byref(g), ptr(a1), 3, 2, ftype, ptr(fb1), ptr(bb1), None)
+    assert _rel(a1, a0) < _tol(real_t) and _rel(fb1, fb0) < _tol(real_t)
+
+
+def test_penalise_is_bit_exact(setup3d):
+    from sopht_mpi_b200.numeric.eulerian_grid_ops.ops import _penalise_factor_table
+
+    real_t, rng, n, gs, shape, g = setup3d
+    width = 2
+    dx = real_t(1.0 / n[2])
+
+    def line(nl):
+        return np.linspace(dx / 2 - gs * dx, nl * dx - dx / 2 + gs * dx, nl + 2 * gs).astype(real_t)
+
+    xg, yg, zg = line(n[2]), line(n[1]), line(n[0])
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    a0, a1 = w.copy(), w.copy()
+    st.penalise_field_boundary_mpi(a0, width, dx, xg, yg, zg, gs)
+    tab = _penalise_factor_table(real_t, width, dx, gs, [zg, yg, xg])
+    call("sb200_penalise_field_boundary", ctypes.byref(g), ptr(a1), 3, width, ptr(tab), None)
+    assert np.array_equal(a1, a0)
+
+
+def test_reductions_and_fused_velocity(setup3d):
+    real_t, rng, n, gs, shape, g = setup3d
+    vel = (rng.uniform(size=(3,) + shape) - 0.5).astype(real_t)
+    inner = (slice(None),) + (slice(gs, -gs),) * 3
+    out = np.zeros(1, np.float64)
+    call("sb200_max_abs_sum", ctypes.byref(g), ptr(vel), 3, ptr(out), None)
+    assert np.isclose(out[0], np.abs(vel[inner]).sum(axis=0).max(), rtol=1e-6)
+    call("sb200_max", ctypes.byref(g), ptr(vel), 3, ptr(out), None)
+    assert out[0] == vel[inner].max()
+    call("sb200_sum_squares", ctypes.byref(g), ptr(vel), 3, ptr(out), None)
+    assert np.isclose(out[0], (vel[inner].astype(np.float64) ** 2).sum(), rtol=1e-12)
+    psi = rng.uniform(size=(3,) + shape).astype(real_t)
+    u0 = rng.uniform(size=(3,) + shape).astype(real_t)
+    u1 = u0.copy()
+    st.curl_mpi(u0, psi, 0.8, gs)
+    fs = np.array([1.0, 0.5, -0.25])
+    for c in range(3):
+        u0[c] += real_t(fs[c])
+    forcing = rng.uniform(size=(3,) + shape).astype(real_t)
+    call("sb200_velocity_from_stream_function", ctypes.byref(g), ptr(u1), ptr(psi), 0.8,
+         fs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ptr(forcing), ptr(out), None)
+    assert _rel(u1, u0) < _tol(real_t)
+    assert np.abs(forcing).max() == 0
+    assert np.isclose(out[0], np.abs(u0[inner]).sum(axis=0).max(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
+def test_2d_operators(real_t):
+    rng = np.random.default_rng(5)
+    n, gs = (10, 14), 2
+    shape = tuple(v + 2 * gs for v in n)
+    g = _lib.make_grid(2, real_t, gs, n, [1] * 4)
+    inner = (slice(gs, -gs),) * 2
+    # outplane curl on the interior-of-interior, zero ring
+    psi = rng.uniform(size=shape).astype(real_t)
+    u = rng.uniform(size=(2,) + shape).astype(real_t)
+    call("sb200_curl", ctypes.byref(g), ptr(u), ptr(psi), 0.5, None)
+    ref = np.zeros_like(u)
+    ref[0, 3:-3, 3:-3] = real_t(0.5) * (psi[4:-2, 3:-3] - psi[2:-4, 3:-3])
+    ref[1, 3:-3, 3:-3] = -real_t(0.5) * (psi[3:-3, 4:-2] - psi[3:-3, 2:-4])
+    assert _rel(u, ref) < _tol(real_t)
+    # diffusion flux 5 point
+    fl = np.zeros(shape, real_t)
+    call("sb200_diffusion_flux", ctypes.byref(g), ptr(fl), ptr(psi), 0.25, None)
+    ref = np.zeros(shape, real_t)
+    ref[3:-3, 3:-3] = real_t(0.25) * (psi[3:-3, 4:-2] + psi[3:-3, 2:-4] + psi[4:-2, 3:-3]
+                                      + psi[2:-4, 3:-3] - 4 * psi[3:-3, 3:-3])
+    assert _rel(fl, ref) < _tol(real_t)
+    # forcing update: omega += p (dFy/dx - dFx/dy) on [2:-2] cells (plus the ghost strips the slabs touch)
+    w = np.zeros(shape, real_t)
+    f = rng.uniform(size=(2,) + shape).astype(real_t)
+    call("sb200_update_vorticity_from_velocity_forcing", ctypes.byref(g), ptr(w), ptr(f), 2.0, None)
+    ref = real_t(2.0) * (f[1][2:-2, 3:-1] - f[1][2:-2, 1:-3] - f[0][3:-1, 2:-2] + f[0][1:-3, 2:-2])
+    assert _rel(w[inner], ref) < _tol(real_t)
+
+
+IB_FILES = sorted(glob.glob(os.path.join(GOLDEN, "ib_*.npz")))
+
+
+@pytest.mark.parametrize("path", IB_FILES, ids=[os.path.basename(p) for p in IB_FILES])
+def test_ib_kernels_against_reference_golden(path):
+    gd = np.load(path)
+    dim, gs, w = int(gd["dim"]), int(gd["gs"]), int(gd["width"])
+    dx, shift = gd["dx"][()], gd["shift"][()]
+    real_t = type(dx)
+    pos = gd["pos"]
+    lag_t = pos.dtype.type
+    n_local = gd["eul_vec"].shape[-1] - 2 * gs
+    g = _lib.make_grid(dim, real_t, gs, (n_local,) * dim, [1] * (2 * dim))
+    p = _lib.IBParams()
+    p.lag_dtype = _lib.dtype_code(lag_t)
+    p.kernel_type = 0
+    p.width = w
+    ss = list(gd["substart_xyz"]) + [0] * (3 - dim)
+    for i in range(3):
+        p.substart_xyz[i] = int(ss[i])
+    p.dx, p.coord_shift, p.stiffness, p.damping = float(dx), float(shift), -3.0, -0.5
+    n = pos.shape[1]
+    near = np.zeros((dim, n), np.int64)
+    wts = np.zeros(gd["w_cos"].shape, lag_t)
+    u, dv, f = (np.zeros((dim, n), lag_t) for _ in range(3))
+    vel = np.full((dim, n), 0.25, lag_t)
+    dpos = np.full((dim, n), 0.01, lag_t)
+    eul = np.ascontiguousarray(gd["eul_vec"])
+    call("sb200_ib_interact_lag", ctypes.byref(g), ctypes.byref(p), n, ptr(eul), ptr(pos), ptr(vel),
+         ptr(dpos), ptr(near), ptr(wts), ptr(u), ptr(dv), ptr(f), None)
+    tol = 1e-6 if (lag_t == np.float32) else 1e-13
+    assert np.array_equal(near, gd["nearest"])  # bit exact index work
+    assert _rel(wts, gd["w_cos"]) < tol
+    assert _rel(u, gd["e2l_vec"]) < tol
+    assert _rel(f, -3.0 * dpos - 0.5 * (gd["e2l_vec"] - vel)) < 10 * tol
+    p.kernel_type = 1
+    wp = np.zeros_like(wts)
+    call("sb200_ib_interact_lag", ctypes.byref(g), ctypes.byref(p), n, ptr(eul), ptr(pos), ptr(vel),
+         ptr(dpos), ptr(near), ptr(wp), ptr(u), ptr(dv), ptr(f), None)
+    assert _rel(wp, gd["w_pes"]) < max(tol, 1e-7 if real_t == np.float32 else 0)
+    p.kernel_type = 0
+    out = np.zeros_like(gd["l2e_vec"])
+    lagv = np.ascontiguousarray(gd["lag_vec"])
+    call("sb200_ib_spread", ctypes.byref(g), ctypes.byref(p), n, ptr(out), ptr(lagv), ptr(pos), None)
+    assert _rel(out, gd["l2e_vec"]) < (1e-6 if out.dtype == np.float32 else 1e-13)
+    call("sb200_clear_ghost_cells", ctypes.byref(g), ptr(out), dim, None)
+    inner = (slice(None),) + (slice(gs, -gs),) * dim
+    chk = gd["l2e_vec"].copy()
+    keep = chk[inner].copy()
+    chk[...] = 0
+    chk[inner] = keep
+    assert _rel(out, chk) < (1e-6 if out.dtype == np.float32 else 1e-13)
