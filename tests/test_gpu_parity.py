@@ -279,8 +279,9 @@ def test_ib_kernels_with_rank_offset_against_golden(cuda, path):
     near = torch.zeros((dim, n), dtype=torch.int64, device=cuda)
     wts = t(np.zeros_like(gd["w_cos"]))
     u = t(np.zeros_like(pos))
-    _lib.check(lib, lib.sb200_ib_interact_lag(ctypes.byref(g), ctypes.byref(p), n, dptr(t(gd["eul_vec"])),
-                                              dptr(t(pos)), None, None, dptr(near), dptr(wts), dptr(u),
+    eul_d, pos_d = t(gd["eul_vec"]), t(pos)  # keep the device buffers alive across the launch
+    _lib.check(lib, lib.sb200_ib_interact_lag(ctypes.byref(g), ctypes.byref(p), n, dptr(eul_d),
+                                              dptr(pos_d), None, None, dptr(near), dptr(wts), dptr(u),
                                               None, None, None))
     torch.cuda.synchronize()
     tol = 1e-5 if pos.dtype == np.float32 else 1e-10
