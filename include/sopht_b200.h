@@ -133,6 +133,8 @@ int sb200_poisson_destroy(sb200_poisson_t* p);
 /* single-rank solve of `ncomp` components: psi interior <- solve(rhs interior) */
 int sb200_poisson_solve(sb200_poisson_t* p, void* solution, const void* rhs, int ncomp, void* stream);
 int64_t sb200_poisson_workspace_bytes(const sb200_poisson_t* p);
+/* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
+int sb200_poisson_fft_available(void);
 
 /* ---- immersed boundary ------------------------------------------------------
  * numeric/immersed_boundary_ops/EulerianLagrangianGridCommunicatorMPI3D.py:116-589

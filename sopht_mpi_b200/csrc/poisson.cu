@@ -3,51 +3,15 @@
 
 #include <vector>
 
-#ifndef SB200_EMU
-#define SB_RN_MUL_F(a, b) __fmul_rn(a, b)
-#define SB_RN_ADD_F(a, b) __fadd_rn(a, b)
-#define SB_RN_MUL_D(a, b) __dmul_rn(a, b)
-#define SB_RN_ADD_D(a, b) __dadd_rn(a, b)
-#else
-#define SB_RN_MUL_F(a, b) ((a) * (b))
-#define SB_RN_ADD_F(a, b) ((a) + (b))
-#define SB_RN_MUL_D(a, b) ((a) * (b))
-#define SB_RN_ADD_D(a, b) ((a) + (b))
-#endif
-// individually rounded ops (no FMA contraction) so G matches numpy bit for bit
-SB_D float rn_mul(float a, float b) { return SB_RN_MUL_F(a, b); }
-SB_D float rn_add(float a, float b) { return SB_RN_ADD_F(a, b); }
-SB_D double rn_mul(double a, double b) { return SB_RN_MUL_D(a, b); }
-SB_D double rn_add(double a, double b) { return SB_RN_ADD_D(a, b); }
-
 template <typename T>
-struct GreensOp {
+struct GreensFillOp {
   T* dst;
-  const T* xl;
-  const T* yl;
-  const T* zl;
-  int dim;
+  SbGreens<T> g;
   long long n2y, n2x;
-  T two_xr, two_yr, two_zr;
-  T four_pi, two_pi;
-  T g0;
   SB_D void operator()(long long i) const {
     const long long x = i % n2x;
     const long long r = i / n2x;
-    const long long y = r % n2y, z = r / n2y;
-    const T xv = xl[x], yv = yl[y];
-    const T ex = fmin(xv, two_xr - xv), ey = fmin(yv, two_yr - yv);
-    T r2 = rn_add(rn_mul(ex, ex), rn_mul(ey, ey));
-    T g;
-    if (dim == 3) {
-      const T zv = zl[z];
-      const T ez = fmin(zv, two_zr - zv);
-      r2 = rn_add(r2, rn_mul(ez, ez));
-      g = (T(1) / sqrt(r2)) / four_pi;
-    } else {
-      g = -log(sqrt(r2)) / two_pi;
-    }
-    dst[i] = i == 0 ? g0 : g;
+    dst[i] = g(r / n2y, r % n2y, x);
   }
 };
 
@@ -61,7 +25,7 @@ static void sb_linspace_line(std::vector<double>& out, int n2, double dx) {
 }
 
 template <typename T>
-static int fill_greens_t(const sb200_poisson* p, void* dst, void* stream) {
+int sb_poisson_make_greens(const sb200_poisson* p, SbGreens<T>* op, void** lines_dev, void* stream) {
   const int n2z = p->dim == 3 ? 2 * p->nz : 1, n2y = 2 * p->ny, n2x = 2 * p->nx;
   std::vector<double> lx, ly, lz;
   sb_linspace_line(lx, n2x, p->dx);
@@ -76,31 +40,53 @@ static int fill_greens_t(const sb200_poisson* p, void* dst, void* stream) {
 #ifndef SB200_EMU
   if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) { sb_set_error("greens: cudaMalloc"); return -2; }
   cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
 #else
-  d = h.data();
+  d = (T*)malloc(h.size() * sizeof(T));
+  memcpy(d, h.data(), h.size() * sizeof(T));
 #endif
-  GreensOp<T> op;
+  *lines_dev = d;
+  op->xl = d;
+  op->yl = d + lx.size();
+  op->zl = d + lx.size() + ly.size();
+  op->dim = p->dim;
+  op->two_xr = (T)(2 * p->x_range);
+  op->two_yr = (T)(2 * p->y_range);
+  op->two_zr = (T)(2 * p->z_range);
+  op->four_pi = (T)(4 * M_PI);
+  op->two_pi = (T)(2 * M_PI);
+  if (p->dim == 3)
+    op->g0 = (T)(1.0 / (4 * M_PI * p->dx));
+  else
+    op->g0 = (T)(-(2 * std::log(p->dx / std::sqrt(M_PI)) - 1) / (4 * M_PI));
+  return 0;
+}
+template int sb_poisson_make_greens<float>(const sb200_poisson*, SbGreens<float>*, void**, void*);
+template int sb_poisson_make_greens<double>(const sb200_poisson*, SbGreens<double>*, void**, void*);
+
+void sb_poisson_free_greens_lines(void* d) {
+#ifndef SB200_EMU
+  cudaFree(d);
+#else
+  free(d);
+#endif
+}
+
+template <typename T>
+static int fill_greens_t(const sb200_poisson* p, void* dst, void* stream) {
+  const int n2z = p->dim == 3 ? 2 * p->nz : 1, n2y = 2 * p->ny, n2x = 2 * p->nx;
+  GreensFillOp<T> op;
+  void* lines = nullptr;
+  int e = sb_poisson_make_greens<T>(p, &op.g, &lines, stream);
+  if (e) return e;
   op.dst = (T*)dst;
-  op.xl = d;
-  op.yl = d + lx.size();
-  op.zl = d + lx.size() + ly.size();
-  op.dim = p->dim;
   op.n2y = n2y;
   op.n2x = n2x;
-  op.two_xr = (T)(2 * p->x_range);
-  op.two_yr = (T)(2 * p->y_range);
-  op.two_zr = (T)(2 * p->z_range);
-  op.four_pi = (T)(4 * M_PI);
-  op.two_pi = (T)(2 * M_PI);
-  if (p->dim == 3)
-    op.g0 = (T)(1.0 / (4 * M_PI * p->dx));
-  else
-    op.g0 = (T)(-(2 * std::log(p->dx / std::sqrt(M_PI)) - 1) / (4 * M_PI));
-  int e = sb_launch_flat((long long)n2z * n2y * n2x, op, stream, "greens");
+  e = sb_launch_flat((long long)n2z * n2y * n2x, op, stream, "greens");
 #ifndef SB200_EMU
   cudaStreamSynchronize((cudaStream_t)stream);
-  cudaFree(d);
 #endif
+  sb_poisson_free_greens_lines(lines);
   return e;
 }
 

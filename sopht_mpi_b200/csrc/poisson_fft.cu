@@ -1,6 +1,434 @@
-// placeholder for the pruned in-kernel FFT pipeline (filled in below)
+// Unbounded Poisson solve, hot-path backend: zero-padding-PRUNED three-pass transform with
+// in-kernel FFTs (fft_device.h).  Per component and cell (W = bytes per real):
+//   x pass   r2c   : read 1W  write 2W      (rows of nx reals -> nx+1 bins, half-length FFT)
+//   y pass   fwd   : read 2W  write 4W      (ny -> 2ny, upper half of the input is zero)
+//   z pass   fused : read 4W  write 4W      (nz -> 2nz fwd, x Ghat, inverse, keep nz) in place
+//   y pass   inv   : read 4W  write 2W
+//   x pass   c2r   : read 2W  write 1W      (straight into the padded solution field)
+// = 26 W, plus the Green's spectrum stored REAL and mirror-compressed to (nz+1)(ny+1)(nx+1)
+// (~1 W per cell per component).  No doubled-domain buffer is ever materialised.
+// Reference semantics: UnboundedPoissonSolverMPI3D.py:133-167 (+ fft_mpi_3d.py:34-48):
+// psi = irfftn(rfftn(pad0(omega)) * rfftn(G) * dx^3)[:nz,:ny,:nx].
+#include "fft_device.h"
 #include "poisson.h"
-int sb_poisson_fft_create(sb200_poisson*, void*) { sb_set_error("fft backend not built"); return -1; }
-int sb_poisson_fft_destroy(sb200_poisson*) { return 0; }
-int sb_poisson_fft_solve(sb200_poisson*, void*, const void*, int, void*) { return -1; }
-int64_t sb_poisson_fft_bytes(const sb200_poisson*) { return 0; }
+
+#include <vector>
+
+#ifndef SB200_EMU
+#define SB_DEV_ALLOC(ptr, bytes) (cudaMalloc((void**)&(ptr), (bytes)) == cudaSuccess)
+#define SB_DEV_FREE(ptr) cudaFree(ptr)
+#define SB_DEV_UPLOAD(dst, src, bytes, stream) \
+  cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)(stream))
+#define SB_STREAM_SYNC(stream) cudaStreamSynchronize((cudaStream_t)(stream))
+#else
+#define SB_DEV_ALLOC(ptr, bytes) (((ptr) = (decltype(ptr))malloc(bytes)) != nullptr)
+#define SB_DEV_FREE(ptr) free(ptr)
+#define SB_DEV_UPLOAD(dst, src, bytes, stream) memcpy(dst, src, bytes)
+#define SB_STREAM_SYNC(stream) (void)0
+#endif
+
+// base offset of line L:  i = L % inner, o1 = (L / inner) % n1, o2 = L / (inner*n1)
+struct SbLines {
+  int inner, n1;
+  long long s0, s1, s2;  // element strides of i, o1, o2
+  long long pt;          // stride between consecutive points of a line
+};
+
+// ------------------------------------------------------------- row loaders (x pass)
+template <typename T>
+struct FieldRowLoader {
+  const T* f;  // padded field(s) (ncomp, mz, my, mx)
+  int nz, ny, gs, dim;
+  long long my, mx, vol;
+  // line = (c*nz + z)*ny + y ; returns (x[2m], x[2m+1]) of the interior row
+  SB_D C2<T> operator()(long long line, int m) const {
+    const long long y = line % ny, r = line / ny;
+    const long long z = r % nz, c = r / nz;
+    const long long row = dim == 3 ? c * vol + ((z + gs) * my + (y + gs)) * mx + gs
+                                   : c * vol + (y + gs) * mx + gs;
+    const T* p = f + row + 2 * m;
+    return C2<T>{p[0], p[1]};
+  }
+};
+template <typename T>
+struct GreensRowLoader {
+  SbGreens<T> g;
+  long long n2y;
+  SB_D C2<T> operator()(long long line, int m) const {
+    const long long y = line % n2y, z = line / n2y;
+    return C2<T>{g(z, y, 2 * m), g(z, y, 2 * m + 1)};
+  }
+};
+
+// ------------------------------------------------------------------ x pass: r2c
+// Real rows of length 2N (only the first `2*in_pts*T`... reals non-zero when pruned) ->
+// N+1 bins through ONE complex FFT of length N on z[m] = x[2m] + i x[2m+1]:
+//   X[k] = (Z[k] + conj Z[N-k])/2 - i W_2N^k (Z[k] - conj Z[N-k])/2
+template <typename T, typename Loader>
+__global__ void __launch_bounds__(512)
+    sb_fft_x_r2c_kernel(SbFftPlan plan, int lines_per_block, long long n_lines, Loader ld, C2<T>* out,
+                        long long out_pitch, const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost,
+                        int in_pts) {
+  SB_DYN_SMEM(smem_raw);
+  C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
+  const int Tn = plan.threads, N = plan.n;
+  const int l = threadIdx.x / Tn, t = threadIdx.x % Tn;
+  const long long line = (long long)blockIdx.x * lines_per_block + l;
+  const bool valid = line < n_lines;
+  const int npad = sb_fft_npad(N);
+  C2<T> v[SB_FFT_R];
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p)
+    v[p] = (valid && p < in_pts) ? ld(line, t + p * Tn) : C2<T>{T(0), T(0)};
+  sb_fft_forward<T, false>(v, plan, t, tw, sm, l, lines_per_block, npad);
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p) sm[sb_sidx<false>(l, t + p * Tn, lines_per_block, npad)] = v[p];
+  __syncthreads();
+  if (valid) {
+    C2<T>* row = out + line * out_pitch;
+#pragma unroll
+    for (int p = 0; p < SB_FFT_R; ++p) {
+      const int k = t + p * Tn;
+      const C2<T> zk = v[p];
+      const C2<T> zc = cconj(sm[sb_sidx<false>(l, (N - k) & (N - 1), lines_per_block, npad)]);
+      const C2<T> wd = cmul(wpost[k], csub(zk, zc));
+      const C2<T> s = cadd(zk, zc);
+      row[k] = C2<T>{T(0.5) * (s.x + wd.y), T(0.5) * (s.y - wd.x)};
+    }
+    if (t == 0) row[N] = C2<T>{v[0].x - v[0].y, T(0)};
+  }
+}
+
+// ------------------------------------------------------------------ x pass: c2r
+// N+1 Hermitian bins -> first 2*out_pts*T reals of the (unnormalised) inverse:
+//   Z[k] = (X[k] + conj X[N-k]) + i W_2N^-k (X[k] - conj X[N-k]),  z = ifft_N(Z),
+//   x[2m] = Re z[m], x[2m+1] = Im z[m]
+template <typename T>
+__global__ void __launch_bounds__(512)
+    sb_fft_x_c2r_kernel(SbFftPlan plan, int lines_per_block, long long n_lines, const C2<T>* in,
+                        long long in_pitch, T* out, int nz, int ny, int gs, int dim, long long my,
+                        long long mx, long long vol, const C2<T>* __restrict__ tw,
+                        const C2<T>* __restrict__ wpost, int out_pts) {
+  SB_DYN_SMEM(smem_raw);
+  C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
+  const int Tn = plan.threads, N = plan.n;
+  const int l = threadIdx.x / Tn, t = threadIdx.x % Tn;
+  const long long line = (long long)blockIdx.x * lines_per_block + l;
+  const bool valid = line < n_lines;
+  const int npad = sb_fft_npad(N);
+  const C2<T>* row = in + line * in_pitch;
+  C2<T> v[SB_FFT_R];
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p) {
+    const int k = t + p * Tn;
+    sm[sb_sidx<false>(l, k, lines_per_block, npad)] = valid ? row[k] : C2<T>{T(0), T(0)};
+  }
+  if (t == 0) sm[sb_sidx<false>(l, N, lines_per_block, npad)] = valid ? row[N] : C2<T>{T(0), T(0)};
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p) {
+    const int k = t + p * Tn;
+    const C2<T> xk = sm[sb_sidx<false>(l, k, lines_per_block, npad)];
+    const C2<T> xc = cconj(sm[sb_sidx<false>(l, N - k, lines_per_block, npad)]);
+    const C2<T> wd = cmul(cconj(wpost[k]), csub(xk, xc));
+    const C2<T> s = cadd(xk, xc);
+    v[p] = C2<T>{s.x - wd.y, s.y + wd.x};
+  }
+  __syncthreads();
+  sb_fft_inverse<T, false>(v, plan, t, tw, sm, l, lines_per_block, npad);
+  if (valid) {
+    const long long y = line % ny, r = line / ny;
+    const long long z = r % nz, c = r / nz;
+    T* orow = out + (dim == 3 ? c * vol + ((z + gs) * my + (y + gs)) * mx + gs
+                              : c * vol + (y + gs) * mx + gs);
+#pragma unroll
+    for (int p = 0; p < SB_FFT_R; ++p) {
+      if (p < out_pts) {
+        const int m = t + p * Tn;
+        orow[2 * m] = v[p].x;
+        orow[2 * m + 1] = v[p].y;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------- strided line pass
+// flags: 1 = forward FFT, 2 = multiply by the real Green's table, 4 = inverse FFT.
+// in_pts / out_pts: how many of the 16 per-thread points are read / written (8 = pruned half).
+template <typename T>
+struct SbGreensTable {
+  const T* g;        // [n_pt_half+1][n1_half+1][pitch] reals (mirror compressed)
+  long long g_pt, g_s1;
+};
+
+SB_D long long sb_line_base(const SbLines& L, long long line, int& o1) {
+  const long long i = line % L.inner;
+  const long long r = line / L.inner;
+  o1 = (int)(r % L.n1);
+  return (r / L.n1) * L.s2 + (long long)o1 * L.s1 + i * L.s0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+    sb_fft_strided_kernel(SbFftPlan plan, int lines_per_block, long long n_lines, const C2<T>* in, SbLines lin,
+                          C2<T>* out, SbLines lout, const C2<T>* __restrict__ tw, int flags, int in_pts,
+                          int out_pts, SbGreensTable<T> gt) {
+  SB_DYN_SMEM(smem_raw);
+  C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
+  const int Tn = plan.threads, n = plan.n;
+  const int l = threadIdx.x % lines_per_block, t = threadIdx.x / lines_per_block;
+  const long long line = (long long)blockIdx.x * lines_per_block + l;
+  const bool valid = line < n_lines;
+  const int npad = sb_fft_npad(n);
+  int o1_in = 0, o1_out = 0;
+  const long long bin = valid ? sb_line_base(lin, line, o1_in) : 0;
+  const long long bout = valid ? sb_line_base(lout, line, o1_out) : 0;
+  C2<T> v[SB_FFT_R];
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p)
+    v[p] = (valid && p < in_pts) ? in[bin + (long long)(t + p * Tn) * lin.pt] : C2<T>{T(0), T(0)};
+  if (flags & 1) sb_fft_forward<T, true>(v, plan, t, tw, sm, l, lines_per_block, npad);
+  if (flags & 2) {
+    if (valid) {
+      const long long i = line % lout.inner;
+      const int h1 = lout.n1 / 2;
+      const int m1 = o1_out <= h1 ? o1_out : lout.n1 - o1_out;
+      const T* g = gt.g + (long long)m1 * gt.g_s1 + i;
+#pragma unroll
+      for (int p = 0; p < SB_FFT_R; ++p) {
+        const int k = t + p * Tn;
+        const int mk = k <= n / 2 ? k : n - k;
+        const T s = g[(long long)mk * gt.g_pt];
+        v[p].x *= s;
+        v[p].y *= s;
+      }
+    }
+    if (flags & 1) __syncthreads();  // the forward pass's last shared-memory reads are done
+  }
+  if (flags & 4) sb_fft_inverse<T, true>(v, plan, t, tw, sm, l, lines_per_block, npad);
+  if (valid) {
+#pragma unroll
+    for (int p = 0; p < SB_FFT_R; ++p)
+      if (p < out_pts) out[bout + (long long)(t + p * Tn) * lout.pt] = v[p];
+  }
+}
+
+// Re(spectrum) * scale -> mirror-compressed table
+template <typename T>
+struct GreensExtractOp {
+  T* g;
+  const C2<T>* full;
+  long long pitch, n2y, hy1;  // hy1 = ny + 1 rows kept
+  T scale;
+  SB_D void operator()(long long i) const {
+    const long long kx = i % pitch, r = i / pitch;
+    const long long ky = r % hy1, kz = r / hy1;
+    g[i] = full[(kz * n2y + ky) * pitch + kx].x * scale;
+  }
+};
+
+// --------------------------------------------------------------------- host state
+template <typename T>
+struct SbFftState {
+  SbFftPlan px, py, pz;
+  C2<T>*twx = nullptr, *twy = nullptr, *twz = nullptr, *wpost = nullptr;
+  C2<T>* A = nullptr;  // [ncomp][nz][ny][P]
+  C2<T>* B = nullptr;  // [ncomp][nz][2ny][P]
+  T* G = nullptr;      // [nz+1][ny+1][P]  (2D: [ny+1][P])
+  long long P = 0;
+  size_t bytes = 0;
+  int ncomp_cap = 3;
+};
+
+template <typename T>
+static C2<T>* make_twiddles(int n, int count, double denom, void* stream) {
+  // W[k] = exp(-2 pi i k / denom), k < count
+  std::vector<C2<T>> h(count);
+  for (int k = 0; k < count; ++k) {
+    const double a = -2.0 * M_PI * (double)k / denom;
+    h[k] = C2<T>{(T)std::cos(a), (T)std::sin(a)};
+  }
+  C2<T>* d = nullptr;
+  if (!SB_DEV_ALLOC(d, sizeof(C2<T>) * count)) return nullptr;
+  SB_DEV_UPLOAD(d, h.data(), sizeof(C2<T>) * count, stream);
+  SB_STREAM_SYNC(stream);
+  (void)n;
+  return d;
+}
+
+static int lines_per_block_for(int threads_per_line, size_t elem, bool strided) {
+  int lb = strided ? (elem == 4 ? 8 : 4) : 1;  // >= 64 B contiguous per point for strided passes
+  while (lb * threads_per_line < 128) lb *= 2;
+  while (lb > 1 && lb * threads_per_line > 512) lb /= 2;
+  return lb;
+}
+
+template <typename T, typename Loader>
+static int launch_x_r2c(const SbFftPlan& plan, long long n_lines, const Loader& ld, C2<T>* out,
+                        long long pitch, const C2<T>* tw, const C2<T>* wpost, int in_pts, void* stream) {
+  const int lb = lines_per_block_for(plan.threads, sizeof(T), false);
+  const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
+  SB_KERNEL_ATTR_SMEM((sb_fft_x_r2c_kernel<T, Loader>), smem);
+  const unsigned blocks = (unsigned)((n_lines + lb - 1) / lb);
+  SB_LAUNCH_COOP((sb_fft_x_r2c_kernel<T, Loader>), dim3(blocks), dim3(lb * plan.threads), smem, stream, plan,
+                 lb, n_lines, ld, out, pitch, tw, wpost, in_pts);
+  SB_CHECK_LAUNCH("fft_x_r2c");
+  return 0;
+}
+
+template <typename T>
+static int launch_strided(const SbFftPlan& plan, long long n_lines, const C2<T>* in, const SbLines& lin,
+                          C2<T>* out, const SbLines& lout, const C2<T>* tw, int flags, int in_pts,
+                          int out_pts, const SbGreensTable<T>& gt, void* stream) {
+  const int lb = lines_per_block_for(plan.threads, sizeof(T), true);
+  const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
+  SB_KERNEL_ATTR_SMEM(sb_fft_strided_kernel<T>, smem);
+  const unsigned blocks = (unsigned)((n_lines + lb - 1) / lb);
+  SB_LAUNCH_COOP(sb_fft_strided_kernel<T>, dim3(blocks), dim3(lb * plan.threads), smem, stream, plan, lb,
+                 n_lines, in, lin, out, lout, tw, flags, in_pts, out_pts, gt);
+  SB_CHECK_LAUNCH("fft_strided");
+  return 0;
+}
+
+template <typename T>
+static int fft_create_t(sb200_poisson* p, void* stream) {
+  auto* st = new SbFftState<T>();
+  p->backend_state = st;
+  const int nz = p->nz, ny = p->ny, nx = p->nx;
+  SB_REQUIRE(sb_fft_make_plan(nx, &st->px) == 0 && sb_fft_make_plan(2 * ny, &st->py) == 0 &&
+                 (p->dim == 2 || sb_fft_make_plan(2 * nz, &st->pz) == 0),
+             "fft backend needs power-of-two grid sizes (nx >= 16, ny >= 8, nz >= 8)");
+  SB_REQUIRE(nx <= 4096 && ny <= 2048 && nz <= 2048, "fft backend: grid too large for one line per block");
+  st->P = nx + 2;
+  const long long P = st->P;
+  st->twx = make_twiddles<T>(nx, nx, (double)nx, stream);
+  st->wpost = make_twiddles<T>(nx, nx, 2.0 * nx, stream);
+  st->twy = make_twiddles<T>(2 * ny, 2 * ny, 2.0 * ny, stream);
+  if (p->dim == 3) st->twz = make_twiddles<T>(2 * nz, 2 * nz, 2.0 * nz, stream);
+  SB_REQUIRE(st->twx && st->wpost && st->twy && (p->dim == 2 || st->twz), "fft backend: twiddle allocation");
+  const long long nzz = p->dim == 3 ? nz : 1;
+  const size_t a_bytes = sizeof(C2<T>) * 3 * nzz * ny * P;
+  const size_t b_bytes = p->dim == 3 ? sizeof(C2<T>) * 3 * nzz * 2 * ny * P : 0;
+  const size_t g_bytes = sizeof(T) * (p->dim == 3 ? (nz + 1) : 1) * (ny + 1) * P;
+  SB_REQUIRE(SB_DEV_ALLOC(st->A, a_bytes), "fft backend: cannot allocate x-pass buffer");
+  if (b_bytes) SB_REQUIRE(SB_DEV_ALLOC(st->B, b_bytes), "fft backend: cannot allocate y-pass buffer");
+  SB_REQUIRE(SB_DEV_ALLOC(st->G, g_bytes), "fft backend: cannot allocate Green's table");
+  st->bytes = a_bytes + b_bytes + g_bytes;
+
+  // ---- Green's spectrum: full (un-pruned) transform of G on the doubled grid, real part kept
+  const long long n2z = p->dim == 3 ? 2LL * nz : 1, n2y = 2LL * ny;
+  C2<T>* full = nullptr;
+  SB_REQUIRE(SB_DEV_ALLOC(full, sizeof(C2<T>) * n2z * n2y * P), "fft backend: cannot allocate Green's scratch");
+  GreensRowLoader<T> gl;
+  void* lines_dev = nullptr;
+  int e = sb_poisson_make_greens<T>(p, &gl.g, &lines_dev, stream);
+  if (e) return e;
+  gl.n2y = n2y;
+  // doubled rows have 2nx reals = nx complex points, none pruned
+  if ((e = launch_x_r2c<T>(st->px, n2z * n2y, gl, full, P, st->twx, st->wpost, SB_FFT_R, stream))) return e;
+  SbGreensTable<T> none{nullptr, 0, 0};
+  {
+    SbLines ly{(int)(nx + 1), (int)n2z, 1, n2y * P, 0, P};  // lines (z, kx), points along y
+    if ((e = launch_strided<T>(st->py, n2z * (nx + 1), full, ly, full, ly, st->twy, 1, SB_FFT_R, SB_FFT_R, none,
+                               stream)))
+      return e;
+  }
+  if (p->dim == 3) {
+    SbLines lz{(int)(nx + 1), (int)n2y, 1, P, 0, n2y * P};  // lines (ky, kx), points along z
+    if ((e = launch_strided<T>(st->pz, n2y * (nx + 1), full, lz, full, lz, st->twz, 1, SB_FFT_R, SB_FFT_R, none,
+                               stream)))
+      return e;
+  }
+  double dxp = 1.0;
+  for (int d = 0; d < p->dim; ++d) dxp *= p->dx;
+  const double scale = dxp / ((double)n2z * (double)n2y * 2.0 * (double)nx);
+  const long long hz1 = p->dim == 3 ? nz + 1 : 1;
+  e = sb_launch_flat(hz1 * (ny + 1) * P, GreensExtractOp<T>{st->G, full, P, n2y, (long long)ny + 1, (T)scale},
+                     stream, "greens_extract");
+  SB_STREAM_SYNC(stream);
+  sb_poisson_free_greens_lines(lines_dev);
+  SB_DEV_FREE(full);
+  return e;
+}
+
+template <typename T>
+static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int ncomp, void* stream) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+  SB_REQUIRE(ncomp >= 1 && ncomp <= 3, "poisson_solve: ncomp must be 1..3");
+  const int nz = p->dim == 3 ? p->nz : 1, ny = p->ny, nx = p->nx, gs = p->gs;
+  const long long P = st->P;
+  const long long my = ny + 2 * gs, mx = nx + 2 * gs;
+  const long long vol = (p->dim == 3 ? nz + 2LL * gs : 1) * my * mx;
+  const long long rows = (long long)ncomp * nz * ny;
+  int e;
+  FieldRowLoader<T> ld{(const T*)rhs, nz, ny, gs, p->dim, my, mx, vol};
+  if ((e = launch_x_r2c<T>(st->px, rows, ld, st->A, P, st->twx, st->wpost, SB_FFT_R / 2, stream))) return e;
+  if (p->dim == 3) {
+    SbGreensTable<T> none{nullptr, 0, 0};
+    // y forward: A[c,z][y][kx] -> B[c,z][ky][kx]
+    SbLines la{(int)(nx + 1), ncomp * nz, 1, ny * P, 0, P};
+    SbLines lb{(int)(nx + 1), ncomp * nz, 1, 2LL * ny * P, 0, P};
+    const long long ylines = (long long)ncomp * nz * (nx + 1);
+    if ((e = launch_strided<T>(st->py, ylines, st->A, la, st->B, lb, st->twy, 1, SB_FFT_R / 2, SB_FFT_R, none,
+                               stream)))
+      return e;
+    // z: forward, x Ghat, inverse, in place on B; lines (c, ky, kx)
+    SbLines lz{(int)(nx + 1), 2 * ny, 1, P, (long long)nz * 2 * ny * P, 2LL * ny * P};
+    SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P};
+    if ((e = launch_strided<T>(st->pz, (long long)ncomp * 2 * ny * (nx + 1), st->B, lz, st->B, lz, st->twz, 7,
+                               SB_FFT_R / 2, SB_FFT_R / 2, gt, stream)))
+      return e;
+    // y inverse: B -> A
+    if ((e = launch_strided<T>(st->py, ylines, st->B, lb, st->A, la, st->twy, 4, SB_FFT_R, SB_FFT_R / 2, none,
+                               stream)))
+      return e;
+  } else {
+    // 2D: fused forward / multiply / inverse along y, in place on A; lines (c, kx)
+    SbLines ly{(int)(nx + 1), 1, 1, 0, (long long)ny * P, P};
+    SbGreensTable<T> gt{st->G, P, 0};
+    if ((e = launch_strided<T>(st->py, (long long)ncomp * (nx + 1), st->A, ly, st->A, ly, st->twy, 7,
+                               SB_FFT_R / 2, SB_FFT_R / 2, gt, stream)))
+      return e;
+  }
+  const int lbx = lines_per_block_for(st->px.threads, sizeof(T), false);
+  const size_t smem = (size_t)lbx * sb_fft_npad(st->px.n) * sizeof(C2<T>);
+  SB_KERNEL_ATTR_SMEM(sb_fft_x_c2r_kernel<T>, smem);
+  SB_LAUNCH_COOP(sb_fft_x_c2r_kernel<T>, dim3((unsigned)((rows + lbx - 1) / lbx)), dim3(lbx * st->px.threads),
+                 smem, stream, st->px, lbx, rows, (const C2<T>*)st->A, P, (T*)solution, nz, ny, gs, p->dim, my,
+                 mx, vol, (const C2<T>*)st->twx, (const C2<T>*)st->wpost, SB_FFT_R / 2);
+  SB_CHECK_LAUNCH("fft_x_c2r");
+  return 0;
+}
+
+template <typename T>
+static void fft_destroy_t(sb200_poisson* p) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+  if (!st) return;
+  SB_DEV_FREE(st->twx);
+  SB_DEV_FREE(st->twy);
+  if (st->twz) SB_DEV_FREE(st->twz);
+  SB_DEV_FREE(st->wpost);
+  if (st->A) SB_DEV_FREE(st->A);
+  if (st->B) SB_DEV_FREE(st->B);
+  if (st->G) SB_DEV_FREE(st->G);
+  delete st;
+  p->backend_state = nullptr;
+}
+
+int sb_poisson_fft_create(sb200_poisson* p, void* stream) {
+  SB_REQUIRE(p->nranks == 1, "fft backend: distributed handles use the slab entry points");
+  SB_DISPATCH_DTYPE(p->dtype, return fft_create_t<T>(p, stream));
+}
+int sb_poisson_fft_destroy(sb200_poisson* p) {
+  if (p->dtype == SB200_F32) fft_destroy_t<float>(p); else fft_destroy_t<double>(p);
+  return 0;
+}
+int sb_poisson_fft_solve(sb200_poisson* p, void* solution, const void* rhs, int ncomp, void* stream) {
+  SB_DISPATCH_DTYPE(p->dtype, return fft_solve_t<T>(p, solution, rhs, ncomp, stream));
+}
+int64_t sb_poisson_fft_bytes(const sb200_poisson* p) {
+  if (!p->backend_state) return 0;
+  return p->dtype == SB200_F32 ? (int64_t)((SbFftState<float>*)p->backend_state)->bytes
+                               : (int64_t)((SbFftState<double>*)p->backend_state)->bytes;
+}
+extern "C" int sb200_poisson_fft_available(void) { return 1; }

@@ -32,7 +32,10 @@ class _UnboundedPoissonSolver:
             raise _lib.SophtB200Error("the Poisson solver needs a CUDA device (no CPU fallback)")
         if backend == "auto":
             pow2 = all(_is_pow2(int(g)) for g in grid_size)
-            backend = "fft" if (pow2 and dim == 3 and _fft_backend_available(self.lib)) else "cufft"
+            big_enough = gs3[2] >= 16 and gs3[1] >= 8 and (dim == 2 or gs3[0] >= 8)
+            small_enough = gs3[2] <= 4096 and gs3[1] <= 2048 and gs3[0] <= 2048
+            backend = ("fft" if (pow2 and big_enough and small_enough and mpi_construct.size == 1
+                                 and _fft_backend_available(self.lib)) else "cufft")
         self.backend = backend
         self._handle = ctypes.c_void_p()
         _lib.check(self.lib, self.lib.sb200_poisson_create(
@@ -69,7 +72,7 @@ _FFT_AVAILABLE = None
 
 
 def _fft_backend_available(lib):
-    return bool(getattr(lib, "sb200_poisson_fft_available", lambda: 0)())
+    return bool(lib.sb200_poisson_fft_available())
 
 
 class UnboundedPoissonSolverMPI3D(_UnboundedPoissonSolver):

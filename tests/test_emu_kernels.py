@@ -225,3 +225,56 @@ def test_ib_kernels_against_reference_golden(path):
     chk[...] = 0
     chk[inner] = keep
     assert _rel(out, chk) < (1e-6 if out.dtype == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("real_t,n", [
+    (np.float64, (8, 8, 16)), (np.float32, (16, 8, 32)), (np.float64, (8, 8, 256)),
+    (np.float32, (8, 64, 16)), (np.float64, (128, 8, 16)), (np.float32, (8, 8, 1024)),
+], ids=lambda v: str(v) if isinstance(v, tuple) else v.__name__)
+def test_pruned_fft_poisson_pipeline_3d(real_t, n):
+    """backend 1 (in-kernel pruned FFT pipeline): every Stockham plan shape up to n = 1024
+    against the scipy.fft oracle (which is what the reference's FFT test pins to)."""
+    from emu_util import emu
+    from oracle.poisson import UnboundedPoissonSolverOracle3D
+
+    lib = emu()
+    gs = 2
+    rng = np.random.default_rng(0)
+    h = ctypes.c_void_p()
+    _lib.check(lib, lib.sb200_poisson_create(ctypes.byref(h), 3, _lib.dtype_code(real_t), n[0], n[1], n[2],
+                                             gs, 1.0, 0, 1, 1, None))
+    shape = tuple(v + 2 * gs for v in n)
+    rhs = rng.uniform(size=(2,) + shape).astype(real_t)
+    sol = np.full_like(rhs, 7.0)
+    _lib.check(lib, lib.sb200_poisson_solve(h, ptr(sol), ptr(rhs), 2, None))
+    lib.sb200_poisson_destroy(h)
+    oracle = UnboundedPoissonSolverOracle3D(*n, x_range=1.0, real_t=real_t)
+    ref = np.zeros_like(rhs)
+    for c in range(2):
+        oracle.solve(ref[c], rhs[c], gs)
+    inner = (slice(None),) + (slice(gs, -gs),) * 3
+    assert _rel(sol[inner], ref[inner]) < (1e-13 if real_t == np.float64 else 2e-6)
+    assert np.all(sol[:, 0] == 7.0) and np.all(sol[:, :, :, -1] == 7.0)  # ghosts untouched
+
+
+@pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
+def test_pruned_fft_poisson_pipeline_2d(real_t):
+    from emu_util import emu
+    from oracle.poisson import UnboundedPoissonSolverOracle2D
+
+    lib = emu()
+    gs, n = 2, (16, 32)
+    rng = np.random.default_rng(0)
+    h = ctypes.c_void_p()
+    _lib.check(lib, lib.sb200_poisson_create(ctypes.byref(h), 2, _lib.dtype_code(real_t), 1, n[0], n[1], gs,
+                                             1.0, 0, 1, 1, None))
+    shape = tuple(v + 2 * gs for v in n)
+    rhs = rng.uniform(size=shape).astype(real_t)
+    sol = np.zeros_like(rhs)
+    _lib.check(lib, lib.sb200_poisson_solve(h, ptr(sol), ptr(rhs), 1, None))
+    lib.sb200_poisson_destroy(h)
+    oracle = UnboundedPoissonSolverOracle2D(*n, x_range=1.0, real_t=real_t)
+    ref = np.zeros_like(rhs)
+    oracle.solve(ref, rhs, gs)
+    inner = (slice(gs, -gs),) * 2
+    assert _rel(sol[inner], ref[inner]) < (1e-13 if real_t == np.float64 else 2e-6)
