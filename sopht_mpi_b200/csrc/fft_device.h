@@ -33,6 +33,7 @@ SB_HD C2<T> cmul_mi(C2<T> a) { return C2<T>{a.y, -a.x}; }
 
 struct SbFftPlan {
   int n;        // transform length (power of two, >= 16)
+  int log2n;
   int threads;  // n / 16 threads per line
   int nstages;
   int radix[SB_FFT_MAXSTAGES];
@@ -41,6 +42,8 @@ struct SbFftPlan {
 static inline int sb_fft_make_plan(int n, SbFftPlan* p) {
   if (n < 16 || (n & (n - 1))) return -1;
   p->n = n;
+  p->log2n = 0;
+  while ((1 << p->log2n) < n) ++p->log2n;
   p->threads = n / SB_FFT_R;
   p->nstages = 0;
   int m = n;
@@ -125,42 +128,91 @@ SB_D void dft_small(C2<T>* a) {
   }
 }
 
-// padded shared-memory index of element i of local line l
-template <bool LINE_FASTEST>
-SB_D int sb_sidx(int l, int i, int lines, int npad) {
-  const int ip = i + (i >> 4);
-  return LINE_FASTEST ? ip * lines + l : l * npad + ip;
-}
+// ------------------------------------------------------------------ shared memory view
+// Element i of a line lives at padded position i + (i >> 4) (one pad per 16 elements keeps
+// the radix-16 scatter conflict-free).  LINE_FASTEST interleaves the lines of a block
+// (element-major) so that strided passes read/write whole line groups contiguously; the
+// number of lines per block is a power of two there (shift `ls`).
 SB_HD int sb_fft_npad(int n) { return n + (n >> 4) + 1; }
 
+template <typename T, bool LINE_FASTEST>
+struct SbSmemLine {
+  C2<T>* base;  // points at element 0 of this thread's line
+  int ls;       // log2(lines per block) when LINE_FASTEST, else 0
+  SB_D C2<T>& at_padded(int ip) const { return base[LINE_FASTEST ? (ip << ls) : ip]; }
+  SB_D C2<T>& at(int i) const { return at_padded(i + (i >> 4)); }
+};
+template <typename T, bool LINE_FASTEST>
+SB_D SbSmemLine<T, LINE_FASTEST> sb_smem_line(C2<T>* sm, int l, int lines_shift, int npad) {
+  SbSmemLine<T, LINE_FASTEST> s;
+  s.base = sm + (LINE_FASTEST ? l : l * npad);
+  s.ls = LINE_FASTEST ? lines_shift : 0;
+  return s;
+}
+
+// twiddles w^1..w^(R-1) of one butterfly from log2(R) exact table entries (w^1, w^2, w^4, w^8);
+// the rest are products of at most three of them.
+template <typename T, int R>
+SB_D void sb_twiddle_apply(C2<T>* a, const C2<T>* __restrict__ tw, int step) {
+  const C2<T> w1 = tw[step];
+  a[1] = cmul(a[1], w1);
+  if (R >= 4) {
+    const C2<T> w2 = tw[2 * step];
+    const C2<T> w3 = cmul(w1, w2);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], w3);
+    if (R >= 8) {
+      const C2<T> w4 = tw[4 * step];
+      const C2<T> w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+      a[4] = cmul(a[4], w4);
+      a[5] = cmul(a[5], w5);
+      a[6] = cmul(a[6], w6);
+      a[7] = cmul(a[7], w7);
+      if (R >= 16) {
+        const C2<T> w8 = tw[8 * step];
+        a[8] = cmul(a[8], w8);
+        a[9] = cmul(a[9], cmul(w1, w8));
+        a[10] = cmul(a[10], cmul(w2, w8));
+        a[11] = cmul(a[11], cmul(w3, w8));
+        a[12] = cmul(a[12], cmul(w4, w8));
+        a[13] = cmul(a[13], cmul(w5, w8));
+        a[14] = cmul(a[14], cmul(w6, w8));
+        a[15] = cmul(a[15], cmul(w7, w8));
+      }
+    }
+  }
+}
+
 // One radix-R stage for the butterflies owned by thread t.
-//   v[p] <-> element t + p*T.  Ns = product of the radices already applied.
-// last == false: results go to shared memory (natural Stockham positions), caller syncs and
-// re-reads; last == true: results return to v[] (their natural positions coincide with p).
+//   v[p] <-> element t + p*T.  Ns = 2^ns_shift = product of the radices already applied
+//   (always a power of 16 here: non-final stages are radix 16).
+// last == false (R == 16 only): results go to shared memory at their Stockham positions,
+// the caller syncs and re-reads; last == true: results return to v[].
 template <typename T, int R, bool LINE_FASTEST>
-SB_D void sb_fft_stage(C2<T>* v, int t, int threads, int n, int Ns, bool last, const C2<T>* __restrict__ tw,
-                       C2<T>* sm, int l, int lines, int npad) {
+SB_D void sb_fft_stage(C2<T>* v, int t, int threads, int log2n, int ns_shift, bool last,
+                       const C2<T>* __restrict__ tw, const SbSmemLine<T, LINE_FASTEST>& sl) {
   constexpr int M = SB_FFT_R / R;  // butterflies per thread
+  constexpr int LOG2R = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
+  const int Ns = 1 << ns_shift;
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     C2<T> a[R];
 #pragma unroll
     for (int q = 0; q < R; ++q) a[q] = v[m + M * q];
     const int j = t + m * threads;
-    const int k = j % Ns;  // Ns is a power of two
-    if (Ns > 1) {
-      const int step = k * (n / (Ns * R));
-#pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], tw[step * q]);
-    }
+    const int k = j & (Ns - 1);
+    if (ns_shift > 0) sb_twiddle_apply<T, R>(a, tw, k << (log2n - ns_shift - LOG2R));
     dft_small<T, R>(a);
     if (last) {
 #pragma unroll
       for (int q = 0; q < R; ++q) v[m + M * q] = a[q];
     } else {
-      const int j0 = (j / Ns) * Ns * R + k;
+      // j0 = (j / Ns) * Ns * R + k ; element j0 + q*Ns ; padded: ip0 + q * stride
+      const int j0 = ((j >> ns_shift) << (ns_shift + LOG2R)) + k;
+      const int ip0 = j0 + (j0 >> 4);
+      const int stride = ns_shift == 0 ? 1 : Ns + (Ns >> 4);
 #pragma unroll
-      for (int q = 0; q < R; ++q) sm[sb_sidx<LINE_FASTEST>(l, j0 + q * Ns, lines, npad)] = a[q];
+      for (int q = 0; q < R; ++q) sl.at_padded(ip0 + q * stride) = a[q];
     }
   }
 }
@@ -168,38 +220,44 @@ SB_D void sb_fft_stage(C2<T>* v, int t, int threads, int n, int Ns, bool last, c
 // Forward FFT of the line held in v[] (all threads of the block must call this; the
 // __syncthreads inside are block-wide).  On return v[p] = X[t + p*T].
 template <typename T, bool LINE_FASTEST>
-SB_D void sb_fft_forward(C2<T>* v, const SbFftPlan& plan, int t, const C2<T>* __restrict__ tw, C2<T>* sm,
-                         int l, int lines, int npad) {
-  int Ns = 1;
+SB_D void sb_fft_forward(C2<T>* v, const SbFftPlan& plan, int t, const C2<T>* __restrict__ tw,
+                         const SbSmemLine<T, LINE_FASTEST>& sl) {
+  int ns_shift = 0;
+  const int log2n = plan.log2n, Tn = plan.threads;
   for (int s = 0; s < plan.nstages; ++s) {
     const int r = plan.radix[s];
     const bool last = s == plan.nstages - 1;
     if (r == 16)
-      sb_fft_stage<T, 16, LINE_FASTEST>(v, t, plan.threads, plan.n, Ns, last, tw, sm, l, lines, npad);
+      sb_fft_stage<T, 16, LINE_FASTEST>(v, t, Tn, log2n, ns_shift, last, tw, sl);
     else if (r == 8)
-      sb_fft_stage<T, 8, LINE_FASTEST>(v, t, plan.threads, plan.n, Ns, last, tw, sm, l, lines, npad);
+      sb_fft_stage<T, 8, LINE_FASTEST>(v, t, Tn, log2n, ns_shift, true, tw, sl);
     else if (r == 4)
-      sb_fft_stage<T, 4, LINE_FASTEST>(v, t, plan.threads, plan.n, Ns, last, tw, sm, l, lines, npad);
+      sb_fft_stage<T, 4, LINE_FASTEST>(v, t, Tn, log2n, ns_shift, true, tw, sl);
     else
-      sb_fft_stage<T, 2, LINE_FASTEST>(v, t, plan.threads, plan.n, Ns, last, tw, sm, l, lines, npad);
+      sb_fft_stage<T, 2, LINE_FASTEST>(v, t, Tn, log2n, ns_shift, true, tw, sl);
     if (!last) {
       __syncthreads();
+      if (Tn >= 16) {
+        const int ip0 = t + (t >> 4), stride = Tn + (Tn >> 4);
 #pragma unroll
-      for (int p = 0; p < SB_FFT_R; ++p)
-        v[p] = sm[sb_sidx<LINE_FASTEST>(l, t + p * plan.threads, lines, npad)];
+        for (int p = 0; p < SB_FFT_R; ++p) v[p] = sl.at_padded(ip0 + p * stride);
+      } else {
+#pragma unroll
+        for (int p = 0; p < SB_FFT_R; ++p) v[p] = sl.at(t + p * Tn);
+      }
       __syncthreads();
     }
-    Ns *= r;
+    ns_shift += r == 16 ? 4 : r == 8 ? 3 : r == 4 ? 2 : 1;
   }
 }
 
 // Unnormalised inverse through conj(fft(conj(x))).
 template <typename T, bool LINE_FASTEST>
-SB_D void sb_fft_inverse(C2<T>* v, const SbFftPlan& plan, int t, const C2<T>* __restrict__ tw, C2<T>* sm,
-                         int l, int lines, int npad) {
+SB_D void sb_fft_inverse(C2<T>* v, const SbFftPlan& plan, int t, const C2<T>* __restrict__ tw,
+                         const SbSmemLine<T, LINE_FASTEST>& sl) {
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
-  sb_fft_forward<T, LINE_FASTEST>(v, plan, t, tw, sm, l, lines, npad);
+  sb_fft_forward<T, LINE_FASTEST>(v, plan, t, tw, sl);
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
 }

@@ -27,70 +27,71 @@
 #define SB_STREAM_SYNC(stream) (void)0
 #endif
 
-// base offset of line L:  i = L % inner, o1 = (L / inner) % n1, o2 = L / (inner*n1)
+// A batch of lines: line (i, o1, o2) starts at element  i + o1*s1 + o2*s2  and its points are
+// `pt` elements apart.  The grid is (ceil(inner / lines_per_block), n1, n2): no index division.
 struct SbLines {
-  int inner, n1;
-  long long s0, s1, s2;  // element strides of i, o1, o2
-  long long pt;          // stride between consecutive points of a line
+  int inner, n1, n2;
+  long long s1, s2;
+  long long pt;
 };
 
-// ------------------------------------------------------------- row loaders (x pass)
+// ------------------------------------------------------------- row sources (x pass)
+// rows are addressed (y, z, c) = (blockIdx.x group, blockIdx.y, blockIdx.z)
 template <typename T>
-struct FieldRowLoader {
-  const T* f;  // padded field(s) (ncomp, mz, my, mx)
-  int nz, ny, gs, dim;
+struct FieldRows {
+  T* f;  // padded field(s) (ncomp, mz, my, mx)
+  int ny, gs, dim;
   long long my, mx, vol;
-  // line = (c*nz + z)*ny + y ; returns (x[2m], x[2m+1]) of the interior row
-  SB_D C2<T> operator()(long long line, int m) const {
-    const long long y = line % ny, r = line / ny;
-    const long long z = r % nz, c = r / nz;
-    const long long row = dim == 3 ? c * vol + ((z + gs) * my + (y + gs)) * mx + gs
-                                   : c * vol + (y + gs) * mx + gs;
-    const T* p = f + row + 2 * m;
+  SB_D T* row(int c, int z, int y) const {
+    return f + (dim == 3 ? c * vol + ((long long)(z + gs) * my + (y + gs)) * mx + gs
+                         : c * vol + (long long)(y + gs) * mx + gs);
+  }
+  SB_D C2<T> load(int c, int z, int y, int m) const {
+    const T* p = row(c, z, y) + 2 * m;
+    if ((gs & 1) == 0) return *reinterpret_cast<const C2<T>*>(p);  // rows start on an even element
     return C2<T>{p[0], p[1]};
   }
 };
 template <typename T>
-struct GreensRowLoader {
+struct GreensRows {
   SbGreens<T> g;
-  long long n2y;
-  SB_D C2<T> operator()(long long line, int m) const {
-    const long long y = line % n2y, z = line / n2y;
-    return C2<T>{g(z, y, 2 * m), g(z, y, 2 * m + 1)};
-  }
+  int ny;  // rows per z (= 2 ny of the solver)
+  SB_D C2<T> load(int, int z, int y, int m) const { return C2<T>{g(z, y, 2 * m), g(z, y, 2 * m + 1)}; }
 };
 
 // ------------------------------------------------------------------ x pass: r2c
-// Real rows of length 2N (only the first `2*in_pts*T`... reals non-zero when pruned) ->
-// N+1 bins through ONE complex FFT of length N on z[m] = x[2m] + i x[2m+1]:
+// Real rows of length 2N (second half zero when PRUNED) -> N+1 bins through ONE complex FFT
+// of length N on z[m] = x[2m] + i x[2m+1]:
 //   X[k] = (Z[k] + conj Z[N-k])/2 - i W_2N^k (Z[k] - conj Z[N-k])/2
-template <typename T, typename Loader>
+template <typename T, typename Rows, bool PRUNED>
 __global__ void __launch_bounds__(512)
-    sb_fft_x_r2c_kernel(SbFftPlan plan, int lines_per_block, long long n_lines, Loader ld, C2<T>* out,
-                        long long out_pitch, const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost,
-                        int in_pts) {
+    sb_fft_x_r2c_kernel(SbFftPlan plan, int lines_per_block, Rows rows, C2<T>* out, long long out_pitch,
+                        const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
   const int Tn = plan.threads, N = plan.n;
-  const int l = threadIdx.x / Tn, t = threadIdx.x % Tn;
-  const long long line = (long long)blockIdx.x * lines_per_block + l;
-  const bool valid = line < n_lines;
-  const int npad = sb_fft_npad(N);
+  const int l = threadIdx.x / Tn, t = threadIdx.x - l * Tn;
+  const int y = blockIdx.x * lines_per_block + l;
+  const int z = blockIdx.y, c = blockIdx.z;
+  const bool valid = y < rows.ny;
+  const int yc = valid ? y : rows.ny - 1;  // clamp: every thread runs the FFT, only stores are masked
+  const SbSmemLine<T, false> sl = sb_smem_line<T, false>(sm, l, 0, sb_fft_npad(N));
+  constexpr int IN = PRUNED ? SB_FFT_R / 2 : SB_FFT_R;
   C2<T> v[SB_FFT_R];
 #pragma unroll
-  for (int p = 0; p < SB_FFT_R; ++p)
-    v[p] = (valid && p < in_pts) ? ld(line, t + p * Tn) : C2<T>{T(0), T(0)};
-  sb_fft_forward<T, false>(v, plan, t, tw, sm, l, lines_per_block, npad);
+  for (int p = 0; p < SB_FFT_R; ++p) v[p] = p < IN ? rows.load(c, z, yc, t + p * Tn) : C2<T>{T(0), T(0)};
+  sb_fft_forward<T, false>(v, plan, t, tw, sl);
 #pragma unroll
-  for (int p = 0; p < SB_FFT_R; ++p) sm[sb_sidx<false>(l, t + p * Tn, lines_per_block, npad)] = v[p];
+  for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = v[p];
   __syncthreads();
   if (valid) {
+    const long long line = ((long long)c * gridDim.y + z) * rows.ny + y;
     C2<T>* row = out + line * out_pitch;
 #pragma unroll
     for (int p = 0; p < SB_FFT_R; ++p) {
       const int k = t + p * Tn;
       const C2<T> zk = v[p];
-      const C2<T> zc = cconj(sm[sb_sidx<false>(l, (N - k) & (N - 1), lines_per_block, npad)]);
+      const C2<T> zc = cconj(sl.at((N - k) & (N - 1)));
       const C2<T> wd = cmul(wpost[k], csub(zk, zc));
       const C2<T> s = cadd(zk, zc);
       row[k] = C2<T>{T(0.5) * (s.x + wd.y), T(0.5) * (s.y - wd.x)};
@@ -100,51 +101,47 @@ __global__ void __launch_bounds__(512)
 }
 
 // ------------------------------------------------------------------ x pass: c2r
-// N+1 Hermitian bins -> first 2*out_pts*T reals of the (unnormalised) inverse:
+// N+1 Hermitian bins -> first N reals of the (unnormalised) inverse of length 2N:
 //   Z[k] = (X[k] + conj X[N-k]) + i W_2N^-k (X[k] - conj X[N-k]),  z = ifft_N(Z),
-//   x[2m] = Re z[m], x[2m+1] = Im z[m]
+//   x[2m] = Re z[m], x[2m+1] = Im z[m]   for m < N/2
 template <typename T>
 __global__ void __launch_bounds__(512)
-    sb_fft_x_c2r_kernel(SbFftPlan plan, int lines_per_block, long long n_lines, const C2<T>* in,
-                        long long in_pitch, T* out, int nz, int ny, int gs, int dim, long long my,
-                        long long mx, long long vol, const C2<T>* __restrict__ tw,
-                        const C2<T>* __restrict__ wpost, int out_pts) {
+    sb_fft_x_c2r_kernel(SbFftPlan plan, int lines_per_block, const C2<T>* in, long long in_pitch,
+                        FieldRows<T> rows, const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
   const int Tn = plan.threads, N = plan.n;
-  const int l = threadIdx.x / Tn, t = threadIdx.x % Tn;
-  const long long line = (long long)blockIdx.x * lines_per_block + l;
-  const bool valid = line < n_lines;
-  const int npad = sb_fft_npad(N);
-  const C2<T>* row = in + line * in_pitch;
+  const int l = threadIdx.x / Tn, t = threadIdx.x - l * Tn;
+  const int y = blockIdx.x * lines_per_block + l;
+  const int z = blockIdx.y, c = blockIdx.z;
+  const bool valid = y < rows.ny;
+  const int yc = valid ? y : rows.ny - 1;
+  const SbSmemLine<T, false> sl = sb_smem_line<T, false>(sm, l, 0, sb_fft_npad(N));
+  const C2<T>* row = in + (((long long)c * gridDim.y + z) * rows.ny + yc) * in_pitch;
   C2<T> v[SB_FFT_R];
 #pragma unroll
-  for (int p = 0; p < SB_FFT_R; ++p) {
-    const int k = t + p * Tn;
-    sm[sb_sidx<false>(l, k, lines_per_block, npad)] = valid ? row[k] : C2<T>{T(0), T(0)};
-  }
-  if (t == 0) sm[sb_sidx<false>(l, N, lines_per_block, npad)] = valid ? row[N] : C2<T>{T(0), T(0)};
+  for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = row[t + p * Tn];
+  if (t == 0) sl.at(N) = row[N];
   __syncthreads();
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) {
     const int k = t + p * Tn;
-    const C2<T> xk = sm[sb_sidx<false>(l, k, lines_per_block, npad)];
-    const C2<T> xc = cconj(sm[sb_sidx<false>(l, N - k, lines_per_block, npad)]);
+    const C2<T> xk = sl.at(k);
+    const C2<T> xc = cconj(sl.at(N - k));
     const C2<T> wd = cmul(cconj(wpost[k]), csub(xk, xc));
     const C2<T> s = cadd(xk, xc);
     v[p] = C2<T>{s.x - wd.y, s.y + wd.x};
   }
   __syncthreads();
-  sb_fft_inverse<T, false>(v, plan, t, tw, sm, l, lines_per_block, npad);
+  sb_fft_inverse<T, false>(v, plan, t, tw, sl);
   if (valid) {
-    const long long y = line % ny, r = line / ny;
-    const long long z = r % nz, c = r / nz;
-    T* orow = out + (dim == 3 ? c * vol + ((z + gs) * my + (y + gs)) * mx + gs
-                              : c * vol + (y + gs) * mx + gs);
+    T* orow = rows.row(c, z, y);
 #pragma unroll
-    for (int p = 0; p < SB_FFT_R; ++p) {
-      if (p < out_pts) {
-        const int m = t + p * Tn;
+    for (int p = 0; p < SB_FFT_R / 2; ++p) {
+      const int m = t + p * Tn;
+      if ((rows.gs & 1) == 0) {
+        *reinterpret_cast<C2<T>*>(orow + 2 * m) = v[p];
+      } else {
         orow[2 * m] = v[p].x;
         orow[2 * m + 1] = v[p].y;
       }
@@ -153,63 +150,69 @@ __global__ void __launch_bounds__(512)
 }
 
 // -------------------------------------------------------------- strided line pass
-// flags: 1 = forward FFT, 2 = multiply by the real Green's table, 4 = inverse FFT.
-// in_pts / out_pts: how many of the 16 per-thread points are read / written (8 = pruned half).
+// MODE 0: forward, pruned input (n/2 points read, n written)            -- y forward
+// MODE 1: forward, x real Green's table, inverse, pruned in and out     -- z (2D: y) fused
+// MODE 2: inverse, pruned output (n read, n/2 written)                   -- y inverse
+// MODE 3: forward, nothing pruned                                        -- Green's set-up
 template <typename T>
 struct SbGreensTable {
-  const T* g;        // [n_pt_half+1][n1_half+1][pitch] reals (mirror compressed)
+  const T* g;  // [n_pt_half+1][n1_half+1][pitch] reals (mirror compressed)
   long long g_pt, g_s1;
 };
 
-SB_D long long sb_line_base(const SbLines& L, long long line, int& o1) {
-  const long long i = line % L.inner;
-  const long long r = line / L.inner;
-  o1 = (int)(r % L.n1);
-  return (r / L.n1) * L.s2 + (long long)o1 * L.s1 + i * L.s0;
-}
-
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(512)
-    sb_fft_strided_kernel(SbFftPlan plan, int lines_per_block, long long n_lines, const C2<T>* in, SbLines lin,
-                          C2<T>* out, SbLines lout, const C2<T>* __restrict__ tw, int flags, int in_pts,
-                          int out_pts, SbGreensTable<T> gt) {
+    sb_fft_strided_kernel(SbFftPlan plan, int lb_shift, const C2<T>* in, SbLines lin, C2<T>* out, SbLines lout,
+                          const C2<T>* __restrict__ tw, SbGreensTable<T> gt) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
   const int Tn = plan.threads, n = plan.n;
-  const int l = threadIdx.x % lines_per_block, t = threadIdx.x / lines_per_block;
-  const long long line = (long long)blockIdx.x * lines_per_block + l;
-  const bool valid = line < n_lines;
-  const int npad = sb_fft_npad(n);
-  int o1_in = 0, o1_out = 0;
-  const long long bin = valid ? sb_line_base(lin, line, o1_in) : 0;
-  const long long bout = valid ? sb_line_base(lout, line, o1_out) : 0;
+  const int l = threadIdx.x & ((1 << lb_shift) - 1), t = threadIdx.x >> lb_shift;
+  const int i = (blockIdx.x << lb_shift) + l;
+  const int o1 = blockIdx.y, o2 = blockIdx.z;
+  const bool valid = i < lin.inner;
+  const int ic = valid ? i : lin.inner - 1;
+  const SbSmemLine<T, true> sl = sb_smem_line<T, true>(sm, l, lb_shift, sb_fft_npad(n));
+  constexpr int IN = (MODE == 0 || MODE == 1) ? SB_FFT_R / 2 : SB_FFT_R;
+  constexpr int OUT = (MODE == 1 || MODE == 2) ? SB_FFT_R / 2 : SB_FFT_R;
   C2<T> v[SB_FFT_R];
+  {
+    const C2<T>* gp = in + (ic + o1 * lin.s1 + o2 * lin.s2 + (long long)t * lin.pt);
+    const long long gstride = (long long)Tn * lin.pt;
 #pragma unroll
-  for (int p = 0; p < SB_FFT_R; ++p)
-    v[p] = (valid && p < in_pts) ? in[bin + (long long)(t + p * Tn) * lin.pt] : C2<T>{T(0), T(0)};
-  if (flags & 1) sb_fft_forward<T, true>(v, plan, t, tw, sm, l, lines_per_block, npad);
-  if (flags & 2) {
-    if (valid) {
-      const long long i = line % lout.inner;
-      const int h1 = lout.n1 / 2;
-      const int m1 = o1_out <= h1 ? o1_out : lout.n1 - o1_out;
-      const T* g = gt.g + (long long)m1 * gt.g_s1 + i;
-#pragma unroll
-      for (int p = 0; p < SB_FFT_R; ++p) {
-        const int k = t + p * Tn;
-        const int mk = k <= n / 2 ? k : n - k;
-        const T s = g[(long long)mk * gt.g_pt];
-        v[p].x *= s;
-        v[p].y *= s;
+    for (int p = 0; p < SB_FFT_R; ++p) {
+      if (p < IN) {
+        v[p] = *gp;
+        gp += gstride;
+      } else {
+        v[p] = C2<T>{T(0), T(0)};
       }
     }
-    if (flags & 1) __syncthreads();  // the forward pass's last shared-memory reads are done
   }
-  if (flags & 4) sb_fft_inverse<T, true>(v, plan, t, tw, sm, l, lines_per_block, npad);
-  if (valid) {
+  if (MODE != 2) sb_fft_forward<T, true>(v, plan, t, tw, sl);
+  if (MODE == 1) {
+    const int h1 = lout.n1 >> 1;
+    const int m1 = o1 <= h1 ? o1 : lout.n1 - o1;
+    const T* g = gt.g + ((long long)m1 * gt.g_s1 + ic);
+    const int half = n >> 1;
 #pragma unroll
-    for (int p = 0; p < SB_FFT_R; ++p)
-      if (p < out_pts) out[bout + (long long)(t + p * Tn) * lout.pt] = v[p];
+    for (int p = 0; p < SB_FFT_R; ++p) {
+      const int k = t + p * Tn;
+      const int mk = k <= half ? k : n - k;
+      const T s = g[mk * gt.g_pt];
+      v[p].x *= s;
+      v[p].y *= s;
+    }
+  }
+  if (MODE == 1 || MODE == 2) sb_fft_inverse<T, true>(v, plan, t, tw, sl);
+  if (valid) {
+    C2<T>* gp = out + (i + o1 * lout.s1 + o2 * lout.s2 + (long long)t * lout.pt);
+    const long long gstride = (long long)Tn * lout.pt;
+#pragma unroll
+    for (int p = 0; p < OUT; ++p) {
+      *gp = v[p];
+      gp += gstride;
+    }
   }
 }
 
@@ -263,29 +266,30 @@ static int lines_per_block_for(int threads_per_line, size_t elem, bool strided) 
   return lb;
 }
 
-template <typename T, typename Loader>
-static int launch_x_r2c(const SbFftPlan& plan, long long n_lines, const Loader& ld, C2<T>* out,
-                        long long pitch, const C2<T>* tw, const C2<T>* wpost, int in_pts, void* stream) {
+template <typename T, typename Rows, bool PRUNED>
+static int launch_x_r2c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
+                        long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream) {
   const int lb = lines_per_block_for(plan.threads, sizeof(T), false);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
-  SB_KERNEL_ATTR_SMEM((sb_fft_x_r2c_kernel<T, Loader>), smem);
-  const unsigned blocks = (unsigned)((n_lines + lb - 1) / lb);
-  SB_LAUNCH_COOP((sb_fft_x_r2c_kernel<T, Loader>), dim3(blocks), dim3(lb * plan.threads), smem, stream, plan,
-                 lb, n_lines, ld, out, pitch, tw, wpost, in_pts);
+  SB_KERNEL_ATTR_SMEM((sb_fft_x_r2c_kernel<T, Rows, PRUNED>), smem);
+  const dim3 grid((unsigned)((ny + lb - 1) / lb), (unsigned)nz, (unsigned)ncomp);
+  SB_LAUNCH_COOP((sb_fft_x_r2c_kernel<T, Rows, PRUNED>), grid, dim3(lb * plan.threads), smem, stream, plan, lb,
+                 rows, out, pitch, tw, wpost);
   SB_CHECK_LAUNCH("fft_x_r2c");
   return 0;
 }
 
-template <typename T>
-static int launch_strided(const SbFftPlan& plan, long long n_lines, const C2<T>* in, const SbLines& lin,
-                          C2<T>* out, const SbLines& lout, const C2<T>* tw, int flags, int in_pts,
-                          int out_pts, const SbGreensTable<T>& gt, void* stream) {
+template <typename T, int MODE>
+static int launch_strided(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
+                          const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
   const int lb = lines_per_block_for(plan.threads, sizeof(T), true);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
-  SB_KERNEL_ATTR_SMEM(sb_fft_strided_kernel<T>, smem);
-  const unsigned blocks = (unsigned)((n_lines + lb - 1) / lb);
-  SB_LAUNCH_COOP(sb_fft_strided_kernel<T>, dim3(blocks), dim3(lb * plan.threads), smem, stream, plan, lb,
-                 n_lines, in, lin, out, lout, tw, flags, in_pts, out_pts, gt);
+  SB_KERNEL_ATTR_SMEM((sb_fft_strided_kernel<T, MODE>), smem);
+  int lb_shift = 0;
+  while ((1 << lb_shift) < lb) ++lb_shift;
+  const dim3 grid((unsigned)((lin.inner + lb - 1) / lb), (unsigned)lin.n1, (unsigned)lin.n2);
+  SB_LAUNCH_COOP((sb_fft_strided_kernel<T, MODE>), grid, dim3(lb * plan.threads), smem, stream, plan, lb_shift,
+                 in, lin, out, lout, tw, gt);
   SB_CHECK_LAUNCH("fft_strided");
   return 0;
 }
@@ -319,25 +323,23 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   const long long n2z = p->dim == 3 ? 2LL * nz : 1, n2y = 2LL * ny;
   C2<T>* full = nullptr;
   SB_REQUIRE(SB_DEV_ALLOC(full, sizeof(C2<T>) * n2z * n2y * P), "fft backend: cannot allocate Green's scratch");
-  GreensRowLoader<T> gl;
+  GreensRows<T> gl;
   void* lines_dev = nullptr;
   int e = sb_poisson_make_greens<T>(p, &gl.g, &lines_dev, stream);
   if (e) return e;
-  gl.n2y = n2y;
+  gl.ny = (int)n2y;
   // doubled rows have 2nx reals = nx complex points, none pruned
-  if ((e = launch_x_r2c<T>(st->px, n2z * n2y, gl, full, P, st->twx, st->wpost, SB_FFT_R, stream))) return e;
+  if ((e = launch_x_r2c<T, GreensRows<T>, false>(st->px, (int)n2y, (int)n2z, 1, gl, full, P, st->twx, st->wpost,
+                                                 stream)))
+    return e;
   SbGreensTable<T> none{nullptr, 0, 0};
   {
-    SbLines ly{(int)(nx + 1), (int)n2z, 1, n2y * P, 0, P};  // lines (z, kx), points along y
-    if ((e = launch_strided<T>(st->py, n2z * (nx + 1), full, ly, full, ly, st->twy, 1, SB_FFT_R, SB_FFT_R, none,
-                               stream)))
-      return e;
+    SbLines ly{nx + 1, (int)n2z, 1, n2y * P, 0, P};  // lines (kx, z), points along y
+    if ((e = launch_strided<T, 3>(st->py, full, ly, full, ly, st->twy, none, stream))) return e;
   }
   if (p->dim == 3) {
-    SbLines lz{(int)(nx + 1), (int)n2y, 1, P, 0, n2y * P};  // lines (ky, kx), points along z
-    if ((e = launch_strided<T>(st->pz, n2y * (nx + 1), full, lz, full, lz, st->twz, 1, SB_FFT_R, SB_FFT_R, none,
-                               stream)))
-      return e;
+    SbLines lz{nx + 1, (int)n2y, 1, P, 0, n2y * P};  // lines (kx, ky), points along z
+    if ((e = launch_strided<T, 3>(st->pz, full, lz, full, lz, st->twz, none, stream))) return e;
   }
   double dxp = 1.0;
   for (int d = 0; d < p->dim; ++d) dxp *= p->dx;
@@ -359,43 +361,35 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
   const long long P = st->P;
   const long long my = ny + 2 * gs, mx = nx + 2 * gs;
   const long long vol = (p->dim == 3 ? nz + 2LL * gs : 1) * my * mx;
-  const long long rows = (long long)ncomp * nz * ny;
   int e;
-  FieldRowLoader<T> ld{(const T*)rhs, nz, ny, gs, p->dim, my, mx, vol};
-  if ((e = launch_x_r2c<T>(st->px, rows, ld, st->A, P, st->twx, st->wpost, SB_FFT_R / 2, stream))) return e;
+  FieldRows<T> src{(T*)rhs, ny, gs, p->dim, my, mx, vol};
+  if ((e = launch_x_r2c<T, FieldRows<T>, true>(st->px, ny, nz, ncomp, src, st->A, P, st->twx, st->wpost, stream)))
+    return e;
+  SbGreensTable<T> none{nullptr, 0, 0};
   if (p->dim == 3) {
-    SbGreensTable<T> none{nullptr, 0, 0};
-    // y forward: A[c,z][y][kx] -> B[c,z][ky][kx]
-    SbLines la{(int)(nx + 1), ncomp * nz, 1, ny * P, 0, P};
-    SbLines lb{(int)(nx + 1), ncomp * nz, 1, 2LL * ny * P, 0, P};
-    const long long ylines = (long long)ncomp * nz * (nx + 1);
-    if ((e = launch_strided<T>(st->py, ylines, st->A, la, st->B, lb, st->twy, 1, SB_FFT_R / 2, SB_FFT_R, none,
-                               stream)))
-      return e;
-    // z: forward, x Ghat, inverse, in place on B; lines (c, ky, kx)
-    SbLines lz{(int)(nx + 1), 2 * ny, 1, P, (long long)nz * 2 * ny * P, 2LL * ny * P};
+    // y forward: A[c][z][y][kx] -> B[c][z][ky][kx]
+    SbLines la{nx + 1, nz, ncomp, (long long)ny * P, (long long)nz * ny * P, P};
+    SbLines lb{nx + 1, nz, ncomp, 2LL * ny * P, 2LL * nz * ny * P, P};
+    if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
+    // z: forward, x Ghat, inverse, in place on B; lines (kx, ky, c)
+    SbLines lz{nx + 1, 2 * ny, ncomp, P, 2LL * nz * ny * P, 2LL * ny * P};
     SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P};
-    if ((e = launch_strided<T>(st->pz, (long long)ncomp * 2 * ny * (nx + 1), st->B, lz, st->B, lz, st->twz, 7,
-                               SB_FFT_R / 2, SB_FFT_R / 2, gt, stream)))
-      return e;
+    if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
     // y inverse: B -> A
-    if ((e = launch_strided<T>(st->py, ylines, st->B, lb, st->A, la, st->twy, 4, SB_FFT_R, SB_FFT_R / 2, none,
-                               stream)))
-      return e;
+    if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
   } else {
-    // 2D: fused forward / multiply / inverse along y, in place on A; lines (c, kx)
-    SbLines ly{(int)(nx + 1), 1, 1, 0, (long long)ny * P, P};
+    // 2D: fused forward / multiply / inverse along y, in place on A; lines (kx, -, c)
+    SbLines ly{nx + 1, 1, ncomp, 0, (long long)ny * P, P};
     SbGreensTable<T> gt{st->G, P, 0};
-    if ((e = launch_strided<T>(st->py, (long long)ncomp * (nx + 1), st->A, ly, st->A, ly, st->twy, 7,
-                               SB_FFT_R / 2, SB_FFT_R / 2, gt, stream)))
-      return e;
+    if ((e = launch_strided<T, 1>(st->py, st->A, ly, st->A, ly, st->twy, gt, stream))) return e;
   }
   const int lbx = lines_per_block_for(st->px.threads, sizeof(T), false);
   const size_t smem = (size_t)lbx * sb_fft_npad(st->px.n) * sizeof(C2<T>);
   SB_KERNEL_ATTR_SMEM(sb_fft_x_c2r_kernel<T>, smem);
-  SB_LAUNCH_COOP(sb_fft_x_c2r_kernel<T>, dim3((unsigned)((rows + lbx - 1) / lbx)), dim3(lbx * st->px.threads),
-                 smem, stream, st->px, lbx, rows, (const C2<T>*)st->A, P, (T*)solution, nz, ny, gs, p->dim, my,
-                 mx, vol, (const C2<T>*)st->twx, (const C2<T>*)st->wpost, SB_FFT_R / 2);
+  FieldRows<T> dst{(T*)solution, ny, gs, p->dim, my, mx, vol};
+  SB_LAUNCH_COOP(sb_fft_x_c2r_kernel<T>, dim3((unsigned)((ny + lbx - 1) / lbx), (unsigned)nz, (unsigned)ncomp),
+                 dim3(lbx * st->px.threads), smem, stream, st->px, lbx, (const C2<T>*)st->A, P, dst,
+                 (const C2<T>*)st->twx, (const C2<T>*)st->wpost);
   SB_CHECK_LAUNCH("fft_x_c2r");
   return 0;
 }

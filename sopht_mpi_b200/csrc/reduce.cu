@@ -41,10 +41,11 @@ SB_D double sb_block_reduce(double v) {
 
 // mode 0: max of sum_c |f_c| ; 1: signed max over comps ; 2: sum of squares
 template <typename T, int MODE>
-__global__ void __launch_bounds__(512) sb_reduce_kernel(SbGeom g, const T* f, int ncomp, void* out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z * blockDim.z + threadIdx.z;
+__global__ void __launch_bounds__(256) sb_reduce_kernel(SbGeom g, const T* f, int ncomp, void* out) {
+  const long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int z = blockIdx.y;
+  const int y = pidx < g.plane ? (int)(pidx / g.mx) : g.my;
+  const int x = pidx < g.plane ? (int)(pidx - (long long)y * g.mx) : g.mx;
   double v = MODE == 2 ? 0.0 : -1.0e300;
   if (x < g.mx && y < g.my && z < g.mz && g.interior(z, y, x)) {
     const long long i = g.idx(z, y, x);
@@ -88,9 +89,8 @@ static int sb_reduce(const sb200_grid_t* gr, const void* field, int ncomp, void*
   SB_REQUIRE(out && field, "reduce: null pointer");
   int e = sb_memset_async(out, 0, 8, stream);
   SB_REQUIRE(e == 0, "reduce: memset failed");
-  dim3 block(64, 4, g.dim == 3 ? 2 : 1);
-  dim3 grid((g.mx + block.x - 1) / block.x, (g.my + block.y - 1) / block.y,
-            (g.mz + block.z - 1) / block.z);
+  dim3 block(256);
+  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)g.mz);
   if (gr->dtype == SB200_F32) {
     SB_LAUNCH_COOP((sb_reduce_kernel<float, MODE>), grid, block, 0, stream, g, (const float*)field,
                    ncomp, out);
@@ -121,11 +121,12 @@ extern "C" int sb200_sum_squares(const sb200_grid_t* g, const void* f, int ncomp
 // F = 0; max over interior of sum_c |u_c|  -- one read of psi, one write of u.
 // (reference flow_simulators_mpi_3d.py:388-393, 422-424, 429-442)
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
     sb_velocity_kernel(SbGeom g, T* u, const T* psi, T p, T u0, T u1, T u2, T* forcing, void* max_out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z * blockDim.z + threadIdx.z;
+  const long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int z = blockIdx.y;
+  const int y = pidx < g.plane ? (int)(pidx / g.mx) : g.my;
+  const int x = pidx < g.plane ? (int)(pidx - (long long)y * g.mx) : g.mx;
   double v = -1.0e300;
   if (x < g.mx && y < g.my && z < g.mz) {
     const long long i = g.idx(z, y, x);
@@ -183,9 +184,8 @@ extern "C" int sb200_velocity_from_stream_function(const sb200_grid_t* gr, void*
     int e = sb_memset_async(max_out, 0, 8, stream);
     SB_REQUIRE(e == 0, "velocity: memset failed");
   }
-  dim3 block(64, 4, g.dim == 3 ? 2 : 1);
-  dim3 grid((g.mx + block.x - 1) / block.x, (g.my + block.y - 1) / block.y,
-            (g.mz + block.z - 1) / block.z);
+  dim3 block(256);
+  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)g.mz);
   if (gr->dtype == SB200_F32) {
     SB_LAUNCH_COOP(sb_velocity_kernel<float>, grid, block, 0, stream, g, (float*)velocity,
                    (const float*)stream_func, (float)prefactor, (float)fs[0], (float)fs[1], (float)fs[2],

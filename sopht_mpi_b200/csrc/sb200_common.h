@@ -77,21 +77,58 @@ static inline int sb_make_geom(const sb200_grid_t* g, SbGeom* o) {
   return 0;
 }
 
-// one thread per cell, x fastest
+// one thread per cell; threads run over the flattened (y,x) plane so that blocks stay full
+// whatever the row length, blockIdx.y walks the planes
 template <typename Op>
-__global__ void __launch_bounds__(512) sb_cell_kernel(SbGeom g, Op op) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z * blockDim.z + threadIdx.z;
-  if (x < g.mx && y < g.my && z < g.mz) op(g, z, y, x);
+__global__ void __launch_bounds__(256) sb_cell_kernel(SbGeom g, Op op) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int z = blockIdx.y;
+  if (idx < g.plane) {
+    const int y = (int)(idx / g.mx);
+    const int x = (int)(idx - (long long)y * g.mx);
+    op(g, z, y, x);
+  }
 }
 
 template <typename Op>
 static inline int sb_launch_cells(const SbGeom& g, const Op& op, void* stream, const char* what) {
-  dim3 block(64, 4, g.dim == 3 ? 2 : 1);
-  dim3 grid((g.mx + block.x - 1) / block.x, (g.my + block.y - 1) / block.y,
-            (g.mz + block.z - 1) / block.z);
+  dim3 block(256);
+  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)g.mz);
   SB_LAUNCH(sb_cell_kernel<Op>, grid, block, 0, stream, g, op);
+  SB_CHECK_LAUNCH(what);
+  return 0;
+}
+
+// a list of up to 6 boxes [lo,hi) of cells; one launch, blockIdx.y selects the box
+struct SbBoxes {
+  int n;
+  int lo[6][3], hi[6][3];  // (z,y,x)
+};
+template <typename Op>
+__global__ void __launch_bounds__(256) sb_box_kernel(SbGeom g, SbBoxes b, Op op) {
+  const int k = blockIdx.y;
+  const long long nz = b.hi[k][0] - b.lo[k][0], ny = b.hi[k][1] - b.lo[k][1], nx = b.hi[k][2] - b.lo[k][2];
+  const long long count = nz * ny * nx;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % nx);
+    const long long r = i / nx;
+    op(g, b.lo[k][0] + (int)(r / ny), b.lo[k][1] + (int)(r % ny), b.lo[k][2] + x);
+  }
+}
+template <typename Op>
+static inline int sb_launch_boxes(const SbGeom& g, const SbBoxes& b, const Op& op, void* stream,
+                                  const char* what) {
+  long long most = 0;
+  for (int k = 0; k < b.n; ++k) {
+    long long c = 1;
+    for (int d = 0; d < 3; ++d) c *= (b.hi[k][d] > b.lo[k][d] ? b.hi[k][d] - b.lo[k][d] : 0);
+    most = c > most ? c : most;
+  }
+  if (b.n == 0 || most == 0) return 0;
+  long long blocks = (most + 255) / 256;
+  if (blocks > 2048) blocks = 2048;
+  SB_LAUNCH(sb_box_kernel<Op>, dim3((unsigned)blocks, (unsigned)b.n), dim3(256), 0, stream, g, b, op);
   SB_CHECK_LAUNCH(what);
   return 0;
 }

@@ -486,10 +486,30 @@ extern "C" int sb200_penalise_field_boundary(const sb200_grid_t* gr, void* field
   if (width == 0) return 0;
   const int w = g.gs + width;
   SB_REQUIRE(g.mx >= 2 * w && g.my >= 2 * w && (g.dim == 2 || g.mz >= 2 * w), "penalty zones overlap");
+  // the penalty zone as disjoint boxes: x slabs (all z,y), y slabs (x in the middle),
+  // z slabs (y,x in the middle)
+  SbBoxes b;
+  b.n = 0;
+  auto add = [&](int z0, int z1, int y0, int y1, int x0, int x1) {
+    const int lo[3] = {z0, y0, x0}, hi[3] = {z1, y1, x1};
+    for (int d = 0; d < 3; ++d) {
+      b.lo[b.n][d] = lo[d];
+      b.hi[b.n][d] = hi[d];
+    }
+    ++b.n;
+  };
+  const int xl = g.phys[4] ? w : 0, xh = g.phys[5] ? g.mx - w : g.mx;
+  const int yl = g.phys[2] ? w : 0, yh = g.phys[3] ? g.my - w : g.my;
+  if (g.phys[4]) add(0, g.mz, 0, g.my, 0, w);
+  if (g.phys[5]) add(0, g.mz, 0, g.my, g.mx - w, g.mx);
+  if (g.phys[2]) add(0, g.mz, 0, w, xl, xh);
+  if (g.phys[3]) add(0, g.mz, g.my - w, g.my, xl, xh);
+  if (g.dim == 3 && g.phys[0]) add(0, w, yl, yh, xl, xh);
+  if (g.dim == 3 && g.phys[1]) add(g.mz - w, g.mz, yl, yh, xl, xh);
   for (int c = 0; c < ncomp; ++c)
     for (int phase = 0; phase < 2; ++phase) {
       int e = 0;
-      SB_DISPATCH_DTYPE(gr->dtype, e = sb_launch_cells(g,
+      SB_DISPATCH_DTYPE(gr->dtype, e = sb_launch_boxes(g, b,
                                                        PenaliseOp<T>{(T*)field + (size_t)c * g.vol,
                                                                      (const T*)factors, w, phase},
                                                        stream, "penalise"));

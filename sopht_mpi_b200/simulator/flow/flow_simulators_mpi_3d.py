@@ -172,6 +172,7 @@ class UnboundedFlowSimulator3D:
             self.buffer_vector_field = zeros_like(self.vorticity_field)
         if self.flow_type == "navier_stokes_with_forcing":
             self.eul_grid_forcing_field = zeros_like(self.velocity_field)
+        self._vorticity_alt = None
         self._max_abs_vel_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._max_abs_vel_version = None
         self._reduce_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -342,25 +343,47 @@ class UnboundedFlowSimulator3D:
     def rotational_form_navier_stokes_timestep(self, dt, free_stream_velocity=None,
                                                _reset_forcing=False):
         """omega += dt curl(u x omega); diffusion; filter; velocity; reference :395-413."""
-        velocity_cross_vorticity = self.buffer_vector_field.view()
-        self.elementwise_cross_product(
-            result_field=velocity_cross_vorticity,
-            field_1=self.velocity_field,
-            field_2=self.vorticity_field,
-        )
-        self.update_vorticity_from_velocity_forcing(
-            vorticity_field=self.vorticity_field,
-            velocity_forcing_field=velocity_cross_vorticity,
-            prefactor=self.real_t(dt / (2 * self.dx)),
-        )
-        self.diffusion_timestep(
-            vector_field=self.vorticity_field,
-            diffusion_flux=self.buffer_scalar_field,
-            nu_dt_by_dx2=self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx),
-        )
+        if self.use_fused_kernels and self.ghost_size >= 2:
+            self._fused_vorticity_update(dt)
+        else:
+            velocity_cross_vorticity = self.buffer_vector_field.view()
+            self.elementwise_cross_product(
+                result_field=velocity_cross_vorticity,
+                field_1=self.velocity_field,
+                field_2=self.vorticity_field,
+            )
+            self.update_vorticity_from_velocity_forcing(
+                vorticity_field=self.vorticity_field,
+                velocity_forcing_field=velocity_cross_vorticity,
+                prefactor=self.real_t(dt / (2 * self.dx)),
+            )
+            self.diffusion_timestep(
+                vector_field=self.vorticity_field,
+                diffusion_flux=self.buffer_scalar_field,
+                nu_dt_by_dx2=self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx),
+            )
         self.filter_vector_field(vector_field=self.vorticity_field)
         self.compute_flow_velocity(free_stream_velocity=free_stream_velocity,
                                    reset_forcing=_reset_forcing)
+
+    def _fused_vorticity_update(self, dt):
+        """cross product + curl update + diffusion in ONE streaming kernel (csrc/fused.cu).
+        Out of place: the result lands in a second vorticity allocation and the two
+        allocations swap roles (every DeviceField wrapping the vorticity tensor follows)."""
+        ctx = self._ctx
+        w, u = self.vorticity_field.tensor, self.velocity_field.tensor
+        if self._vorticity_alt is None:
+            self._vorticity_alt = torch.empty_like(w)
+        if ctx.distributed:
+            # ghost planes of omega and u stand in for the reference's exchanges of u x omega
+            # and of omega between its three sweeps
+            ctx.exchange_vector(w)
+            ctx.exchange_vector(u)
+        alt = self._vorticity_alt
+        ctx.call("sb200_vorticity_rhs_fused_3d", ctx.gref, dptr(alt), dptr(w), dptr(u), None,
+                 float(self.real_t(dt / (2 * self.dx))),
+                 float(self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx)), ctx.stream())
+        w.data, alt.data = alt.data, w.data
 
     def navier_stokes_with_forcing_timestep(self, dt, free_stream_velocity=None):
         """reference :415-424"""

@@ -290,9 +290,10 @@ def test_ib_kernels_with_rank_offset_against_golden(cuda, path):
     assert _rel(u.cpu().numpy(), gd["e2l_vec"]) <= tol
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
 @pytest.mark.parametrize("real_t,steps", [(np.float64, 5), (np.float32, 5)], ids=["f64", "f32"])
 @pytest.mark.parametrize("flow_type", ["navier_stokes_with_forcing", "navier_stokes"])
-def test_simulator_steps_against_oracle(cuda, real_t, steps, flow_type):
+def test_simulator_steps_against_oracle(cuda, real_t, steps, flow_type, fused):
     """N full time steps (same dt fed to both) on a smooth compact vorticity field +
     a smooth forcing: omega, u, psi within the north-star tolerance."""
     from sopht_mpi_b200.simulator import UnboundedFlowSimulator3D
@@ -301,7 +302,7 @@ def test_simulator_steps_against_oracle(cuda, real_t, steps, flow_type):
     kw = dict(grid_size=n, x_range=1.0, kinematic_viscosity=1e-2, flow_type=flow_type, real_t=real_t,
               with_free_stream_flow=True, filter_vorticity=True,
               filter_setting_dict={"order": 1, "type": "multiplicative"})
-    sim = UnboundedFlowSimulator3D(**kw)
+    sim = UnboundedFlowSimulator3D(use_fused_kernels=fused, **kw)
     ora = FlowSimulatorOracle3D(**kw)
     gs = sim.ghost_size
     x, y, z = ora.local_x, ora.local_y, ora.local_z
