@@ -261,3 +261,119 @@ SB_D void sb_fft_inverse(C2<T>* v, const SbFftPlan& plan, int t, const C2<T>* __
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
 }
+
+// =========================================================================================
+// Compile-time specialised transform: n = 2^LOG2N, LINES = lines per block (power of two) when
+// LINE_FASTEST.  Every stride below is a constant, so shared-memory addresses fold into
+// base + immediate and the 16-point register file never moves between code paths.
+template <int LOG2N>
+struct SbFftC {
+  static constexpr int n = 1 << LOG2N;
+  static constexpr int Tn = n / SB_FFT_R;
+  static constexpr int nfull = LOG2N / 4;       // radix-16 stages
+  static constexpr int rem = LOG2N % 4;         // final radix 2^rem stage (if any)
+  static constexpr int npad = n + (n >> 4) + 1;
+};
+
+template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>
+struct SbFftLineC {
+  using P = SbFftC<LOG2N>;
+  static constexpr int MUL = LINE_FASTEST ? LINES : 1;
+  // pointer to padded element 0 of local line l
+  static SB_D C2<T>* line(C2<T>* sm, int l) { return sm + (LINE_FASTEST ? l : l * P::npad); }
+  static SB_HD size_t smem_bytes() { return sizeof(C2<T>) * (size_t)LINES * P::npad; }
+};
+
+template <typename T, int LOG2N, bool LINE_FASTEST, int LINES, int R, int NS_SHIFT, bool LAST>
+SB_D void sb_fft_stage_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+  using P = SbFftC<LOG2N>;
+  constexpr int MUL = LINE_FASTEST ? LINES : 1;
+  constexpr int M = SB_FFT_R / R;
+  constexpr int LOG2R = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
+  constexpr int Ns = 1 << NS_SHIFT;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    C2<T> a[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) a[q] = v[m + M * q];
+    const int j = t + m * P::Tn;
+    const int k = j & (Ns - 1);
+    if constexpr (NS_SHIFT > 0) sb_twiddle_apply<T, R>(a, tw, k << (LOG2N - NS_SHIFT - LOG2R));
+    dft_small<T, R>(a);
+    if constexpr (LAST) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[m + M * q] = a[q];
+    } else {
+      const int j0 = ((j >> NS_SHIFT) << (NS_SHIFT + LOG2R)) + k;
+      C2<T>* dst = sl + (j0 + (j0 >> 4)) * MUL;
+      constexpr int stride = (NS_SHIFT == 0 ? 1 : Ns + (Ns >> 4)) * MUL;
+#pragma unroll
+      for (int q = 0; q < R; ++q) dst[q * stride] = a[q];
+    }
+  }
+}
+
+// shared-memory re-read of the thread's 16 points (positions t + p*Tn)
+template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>
+SB_D void sb_fft_reread_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* sl) {
+  using P = SbFftC<LOG2N>;
+  constexpr int MUL = LINE_FASTEST ? LINES : 1;
+  if constexpr (P::Tn >= 16) {
+    const C2<T>* src = sl + (t + (t >> 4)) * MUL;
+    constexpr int stride = (P::Tn + (P::Tn >> 4)) * MUL;
+#pragma unroll
+    for (int p = 0; p < SB_FFT_R; ++p) v[p] = src[p * stride];
+  } else {
+#pragma unroll
+    for (int p = 0; p < SB_FFT_R; ++p) {
+      const int i = t + p * P::Tn;
+      v[p] = sl[(i + (i >> 4)) * MUL];
+    }
+  }
+}
+
+template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>
+SB_D void sb_fft_forward_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+  using P = SbFftC<LOG2N>;
+  static_assert(LOG2N >= 4 && LOG2N <= 12, "supported lengths: 16 .. 4096");
+  // stage 0
+  if constexpr (P::nfull >= 1) {
+    constexpr bool last = P::nfull == 1 && P::rem == 0;
+    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 0, last>(v, t, tw, sl);
+    if constexpr (!last) {
+      __syncthreads();
+      sb_fft_reread_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, sl);
+      __syncthreads();
+    }
+  }
+  if constexpr (P::nfull >= 2) {
+    constexpr bool last = P::nfull == 2 && P::rem == 0;
+    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 4, last>(v, t, tw, sl);
+    if constexpr (!last) {
+      __syncthreads();
+      sb_fft_reread_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, sl);
+      __syncthreads();
+    }
+  }
+  if constexpr (P::nfull >= 3) {
+    constexpr bool last = P::rem == 0;
+    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 8, last>(v, t, tw, sl);
+    if constexpr (!last) {
+      __syncthreads();
+      sb_fft_reread_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, sl);
+      __syncthreads();
+    }
+  }
+  if constexpr (P::rem == 1) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 2, 4 * P::nfull, true>(v, t, tw, sl);
+  if constexpr (P::rem == 2) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 4, 4 * P::nfull, true>(v, t, tw, sl);
+  if constexpr (P::rem == 3) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 8, 4 * P::nfull, true>(v, t, tw, sl);
+}
+
+template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>
+SB_D void sb_fft_inverse_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
+  sb_fft_forward_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, tw, sl);
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
+}

@@ -7,38 +7,47 @@
 // 2.5D scheme: a CTA owns a (TY x TX) tile of the (y,x) plane and marches along z; the
 // cross product is staged on the tile + 2 halo cells, omega2 on tile + 1, both in rings of
 // three planes in shared memory, so every input plane is read from HBM once (plus the
-// in-plane halo overlap) and the output written once: ~9 W per cell instead of 33 W.
+// in-plane halo overlap, served by L2) and the output written once: ~9 W per cell instead of
+// 33 W.  Each thread owns a fixed set of cells of every region: shared/global offsets and the
+// (y,x) part of the wrapper masks are computed once, the z part is uniform per plane, and the
+// next plane's omega/u are prefetched into registers while the current one is processed.
 #include "sb200_common.h"
 
-template <int TY, int TX>
+template <int TY, int TX, int NT>
 struct FusedTile {
   static constexpr int P2 = TX + 4, R2 = (TY + 4) * P2;  // tile + halo 2
   static constexpr int P1 = TX + 2, R1 = (TY + 2) * P1;  // tile + halo 1
-  // floats: buf ring 3 planes x 3 comps, omega ring 2 x 3, omega2 ring 3 x 3
+  static constexpr int R0 = TY * TX;
+  static constexpr int C2N = (R2 + NT - 1) / NT;  // cells per thread in each region
+  static constexpr int C1N = (R1 + NT - 1) / NT;
+  static constexpr int C0N = (R0 + NT - 1) / NT;
+  // reals: buf ring 3 planes x 3 comps (R2), omega ring 2 x 3 (R1), omega2 ring 3 x 3 (R1)
   static constexpr int ELEMS = 9 * R2 + 6 * R1 + 9 * R1;
 };
 
-// written-cell mask of a support-1 wrapper with the z conditions opened on faces that are
-// NOT physical (inner slab faces): there the ghost planes hold exchanged data and the update
-// applied to them reproduces what the neighbouring slab computes for its own interior.
-SB_D bool sb_written_open(const SbGeom& g, int z, int y, int x) {
+// (y,x) part of the support-1 wrapper mask:
+//   bit0 = A: written whenever 1 <= z < mz-1           (x slabs, y slabs)
+//   bit1 = B: written whenever z is in the interior / z-slab range
+//   bit2 = inside the array, bit3 = on the physical ring because of y or x
+SB_D int sb_yx_mask(const SbGeom& g, int y, int x) {
+  if (y < 0 || y >= g.my || x < 0 || x >= g.mx) return 0;
   const int gs = g.gs;
   const bool xs = (x == gs) || (x == g.mx - gs - 1);
   const bool xi = x > gs && x < g.mx - gs - 1;
   const bool ys = (y == gs) || (y == g.my - gs - 1);
   const bool yi = y > gs && y < g.my - gs - 1;
   const bool yfull = y >= 1 && y < g.my - 1;
-  const bool zfull = z >= 1 && z < g.mz - 1;
-  const int zlo = g.phys[0] ? gs : 1, zhi = g.phys[1] ? g.mz - gs : g.mz - 1;
-  const bool zin = z >= zlo && z < zhi;
-  return (xs && yfull && zfull) || (xi && ys && zfull) || (xi && yi && zin);
+  const int w = gs + 1;
+  const bool ring = (g.phys[4] && x < w) || (g.phys[5] && x >= g.mx - w) || (g.phys[2] && y < w) ||
+                    (g.phys[3] && y >= g.my - w);
+  return ((xs && yfull) || (xi && ys) ? 1 : 0) | (xi && yi ? 2 : 0) | 4 | (ring ? 8 : 0);
 }
 
 template <typename T, int TY, int TX, int NT>
 __global__ void __launch_bounds__(NT)
     sb_vorticity_fused_kernel(SbGeom g, T* __restrict__ out, const T* __restrict__ w, const T* __restrict__ u,
                               T p, T d, int zchunk) {
-  using FT = FusedTile<TY, TX>;
+  using FT = FusedTile<TY, TX, NT>;
   SB_DYN_SMEM(smem_raw);
   T* sbuf = reinterpret_cast<T*>(smem_raw);  // [3][3][R2]
   T* sw1 = sbuf + 9 * FT::R2;                // [2][3][R1]
@@ -47,37 +56,88 @@ __global__ void __launch_bounds__(NT)
   const int y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
   const int zb = blockIdx.z * zchunk;
   const int ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
-  const long long vol = g.vol;
+  const long long vol = g.vol, plane = g.plane;
+  const int zlo = g.phys[0] ? g.gs : 1, zhi = g.phys[1] ? g.mz - g.gs : g.mz - 1;
+  const int zring_lo = g.phys[0] ? g.gs + 1 : 0, zring_hi = g.phys[1] ? g.mz - g.gs - 1 : g.mz;
+
+  // ---- per-thread cell bookkeeping (z invariant)
+  int a_goff[FT::C2N], a_j[FT::C2N];  // region 2: global (y,x) offset (-1 = none), region-1 slot (-1)
+  int b_i[FT::C1N], b_m[FT::C1N];     // region 1: region-2 slot, mask
+  int c_j[FT::C0N], c_goff[FT::C0N], c_m[FT::C0N];
+#pragma unroll
+  for (int k = 0; k < FT::C2N; ++k) {
+    const int i = tid + k * NT;
+    const int ry = i / FT::P2, rx = i - ry * FT::P2;
+    const int y = y0 + ry - 2, x = x0 + rx - 2;
+    const bool in = i < FT::R2 && y >= 0 && y < g.my && x >= 0 && x < g.mx;
+    a_goff[k] = in ? y * g.mx + x : -1;
+    a_j[k] = (i < FT::R2 && ry >= 1 && ry <= TY + 2 && rx >= 1 && rx <= TX + 2)
+                 ? (ry - 1) * FT::P1 + (rx - 1)
+                 : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < FT::C1N; ++k) {
+    const int j = tid + k * NT;
+    const int ry = j / FT::P1, rx = j - ry * FT::P1;
+    b_i[k] = (ry + 1) * FT::P2 + (rx + 1);
+    b_m[k] = j < FT::R1 ? sb_yx_mask(g, y0 + ry - 1, x0 + rx - 1) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < FT::C0N; ++k) {
+    const int c = tid + k * NT;
+    const int ty = c / TX, tx = c - ty * TX;
+    const int y = y0 + ty, x = x0 + tx;
+    c_j[k] = (ty + 1) * FT::P1 + (tx + 1);
+    c_m[k] = c < FT::R0 ? sb_yx_mask(g, y, x) : 0;
+    c_goff[k] = y * g.mx + x;
+  }
+
+  // ---- register prefetch of plane zf: omega (3) and u (3) for this thread's region-2 cells
+  T rw[FT::C2N][3], ru[FT::C2N][3];
+  auto prefetch = [&](int z) {
+    const bool zin = z >= 0 && z < g.mz;
+    const long long zoff = (long long)z * plane;
+#pragma unroll
+    for (int k = 0; k < FT::C2N; ++k) {
+      if (zin && a_goff[k] >= 0) {
+        const long long gi = zoff + a_goff[k];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          rw[k][c] = w[gi + c * vol];
+          ru[k][c] = u[gi + c * vol];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rw[k][c] = ru[k][c] = T(0);
+      }
+    }
+  };
+  prefetch(zb - 2);
 
   for (int zf = zb - 2; zf <= ze + 1; ++zf) {
     // ---- A: cross product of plane zf on tile + 2, omega of plane zf on tile + 1
-    if (zf >= 0 && zf < g.mz) {
-      T* b = sbuf + (zf % 3) * 3 * FT::R2;
-      T* s1 = sw1 + (zf & 1) * 3 * FT::R1;
-      for (int i = tid; i < FT::R2; i += NT) {
-        const int ry = i / FT::P2, rx = i - ry * FT::P2;
-        const int y = y0 + ry - 2, x = x0 + rx - 2;
-        T w0 = 0, w1 = 0, w2 = 0, u0 = 0, u1 = 0, u2 = 0;
-        if (y >= 0 && y < g.my && x >= 0 && x < g.mx) {
-          const long long gi = g.idx(zf, y, x);
-          w0 = w[gi];
-          w1 = w[gi + vol];
-          w2 = w[gi + 2 * vol];
-          u0 = u[gi];
-          u1 = u[gi + vol];
-          u2 = u[gi + 2 * vol];
-        }
-        b[i] = u1 * w2 - u2 * w1;
-        b[FT::R2 + i] = u2 * w0 - u0 * w2;
-        b[2 * FT::R2 + i] = u0 * w1 - u1 * w0;
-        if (ry >= 1 && ry <= TY + 2 && rx >= 1 && rx <= TX + 2) {
-          const int j = (ry - 1) * FT::P1 + (rx - 1);
-          s1[j] = w0;
-          s1[FT::R1 + j] = w1;
-          s1[2 * FT::R1 + j] = w2;
+    {
+      T* b = sbuf + ((zf + 3) % 3) * 3 * FT::R2;
+      T* s1 = sw1 + ((zf + 2) & 1) * 3 * FT::R1;
+#pragma unroll
+      for (int k = 0; k < FT::C2N; ++k) {
+        const int i = tid + k * NT;
+        if (i < FT::R2) {
+          const T w0 = rw[k][0], w1 = rw[k][1], w2 = rw[k][2];
+          const T u0 = ru[k][0], u1 = ru[k][1], u2 = ru[k][2];
+          b[i] = u1 * w2 - u2 * w1;
+          b[FT::R2 + i] = u2 * w0 - u0 * w2;
+          b[2 * FT::R2 + i] = u0 * w1 - u1 * w0;
+          const int j = a_j[k];
+          if (j >= 0) {
+            s1[j] = w0;
+            s1[FT::R1 + j] = w1;
+            s1[2 * FT::R1 + j] = w2;
+          }
         }
       }
     }
+    if (zf + 1 <= ze + 1) prefetch(zf + 1);  // in flight during phases B and C
     __syncthreads();
     // ---- B: omega2 of plane zc = zf - 1 on tile + 1
     const int zc = zf - 1;
@@ -87,22 +147,24 @@ __global__ void __launch_bounds__(NT)
       const T* bp = sbuf + ((zc + 1) % 3) * 3 * FT::R2;
       const T* s1 = sw1 + (zc & 1) * 3 * FT::R1;
       T* s2 = sw2 + (zc % 3) * 3 * FT::R1;
-      for (int j = tid; j < FT::R1; j += NT) {
-        const int ry = j / FT::P1, rx = j - ry * FT::P1;
-        const int y = y0 + ry - 1, x = x0 + rx - 1;
-        T c0 = s1[j], c1 = s1[FT::R1 + j], c2 = s1[2 * FT::R1 + j];
-        if (y >= 0 && y < g.my && x >= 0 && x < g.mx && sb_written_open(g, zc, y, x)) {
-          const int i = (ry + 1) * FT::P2 + (rx + 1);  // same cell in the tile + 2 frame
-          const T* bx0 = b0;
-          const T* by0 = b0 + FT::R2;
-          const T* bz0 = b0 + 2 * FT::R2;
-          c0 += p * (bz0[i + FT::P2] - bz0[i - FT::P2] - bp[FT::R2 + i] + bm[FT::R2 + i]);
-          c1 += p * (bp[i] - bm[i] - bz0[i + 1] + bz0[i - 1]);
-          c2 += p * (by0[i + 1] - by0[i - 1] - bx0[i + FT::P2] + bx0[i - FT::P2]);
+      const int zmask = ((zc >= 1 && zc < g.mz - 1) ? 1 : 0) | ((zc >= zlo && zc < zhi) ? 2 : 0);
+#pragma unroll
+      for (int k = 0; k < FT::C1N; ++k) {
+        const int j = tid + k * NT;
+        if (j < FT::R1) {
+          T c0 = s1[j], c1 = s1[FT::R1 + j], c2 = s1[2 * FT::R1 + j];
+          if (b_m[k] & zmask & 3) {
+            const int i = b_i[k];
+            const T* by0 = b0 + FT::R2;
+            const T* bz0 = b0 + 2 * FT::R2;
+            c0 += p * (bz0[i + FT::P2] - bz0[i - FT::P2] - bp[FT::R2 + i] + bm[FT::R2 + i]);
+            c1 += p * (bp[i] - bm[i] - bz0[i + 1] + bz0[i - 1]);
+            c2 += p * (by0[i + 1] - by0[i - 1] - b0[i + FT::P2] + b0[i - FT::P2]);
+          }
+          s2[j] = c0;
+          s2[FT::R1 + j] = c1;
+          s2[2 * FT::R1 + j] = c2;
         }
-        s2[j] = c0;
-        s2[FT::R1 + j] = c1;
-        s2[2 * FT::R1 + j] = c2;
       }
     }
     __syncthreads();
@@ -112,13 +174,16 @@ __global__ void __launch_bounds__(NT)
       const T* qm = sw2 + ((zo + 2) % 3) * 3 * FT::R1;
       const T* q0 = sw2 + (zo % 3) * 3 * FT::R1;
       const T* qp = sw2 + ((zo + 1) % 3) * 3 * FT::R1;
-      for (int k = tid; k < TY * TX; k += NT) {
-        const int ty = k / TX, tx = k - ty * TX;
-        const int y = y0 + ty, x = x0 + tx;
-        if (y < g.my && x < g.mx) {
-          const int j = (ty + 1) * FT::P1 + (tx + 1);
-          const bool lap = !g.in_ring(zo, y, x) && sb_written_open(g, zo, y, x);
-          const long long gi = g.idx(zo, y, x);
+      const int zmask = ((zo >= 1 && zo < g.mz - 1) ? 1 : 0) | ((zo >= zlo && zo < zhi) ? 2 : 0);
+      const bool zring = zo < zring_lo || zo >= zring_hi;
+      const long long zoff = (long long)zo * plane;
+#pragma unroll
+      for (int k = 0; k < FT::C0N; ++k) {
+        const int m = c_m[k];
+        if (m & 4) {
+          const int j = c_j[k];
+          const bool lap = (m & zmask & 3) && !(m & 8) && !zring;
+          const long long gi = zoff + c_goff[k];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const T* q = q0 + c * FT::R1;
@@ -140,11 +205,11 @@ __global__ void __launch_bounds__(NT)
 template <typename T, int TY, int TX, int NT>
 static int launch_fused(const SbGeom& g, void* out, const void* w, const void* u, double p, double d,
                         void* stream) {
-  using FT = FusedTile<TY, TX>;
+  using FT = FusedTile<TY, TX, NT>;
   const size_t smem = sizeof(T) * FT::ELEMS;
   const unsigned gx = (g.mx + TX - 1) / TX, gy = (g.my + TY - 1) / TY;
-  // enough z chunks for ~2 waves of 148 SMs, each chunk at least 16 planes
-  int chunks = (int)((2 * 148 + gx * gy - 1) / (gx * gy));
+  // enough z chunks for several waves of 148 SMs x resident CTAs, each chunk at least 16 planes
+  int chunks = (int)((6 * 148 + gx * gy - 1) / (gx * gy));
   if (chunks < 1) chunks = 1;
   int zchunk = (g.mz + chunks - 1) / chunks;
   if (zchunk < 16) zchunk = 16;
@@ -168,7 +233,8 @@ extern "C" int sb200_vorticity_rhs_fused_3d(const sb200_grid_t* gr, void* out, c
   SB_REQUIRE(forcing == nullptr,
              "vorticity_rhs_fused_3d: apply the forcing update first "
              "(sb200_update_vorticity_from_velocity_forcing)");
+  SB_REQUIRE(g.plane < (1LL << 31), "vorticity_rhs_fused_3d: plane too large");
   if (gr->dtype == SB200_F32)
-    return launch_fused<float, 16, 64, 512>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
-  return launch_fused<double, 8, 64, 512>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+    return launch_fused<float, 8, 64, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+  return launch_fused<double, 8, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
 }

@@ -63,13 +63,14 @@ struct GreensRows {
 // Real rows of length 2N (second half zero when PRUNED) -> N+1 bins through ONE complex FFT
 // of length N on z[m] = x[2m] + i x[2m+1]:
 //   X[k] = (Z[k] + conj Z[N-k])/2 - i W_2N^k (Z[k] - conj Z[N-k])/2
-template <typename T, typename Rows, bool PRUNED>
-__global__ void __launch_bounds__(512)
-    sb_fft_x_r2c_kernel(SbFftPlan plan, int lines_per_block, Rows rows, C2<T>* out, long long out_pitch,
+template <typename T, typename Rows, bool PRUNED, int LOG2N, int LINES>
+__global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 512)
+    sb_fft_x_r2c_kernel(SbFftPlan plan, int lines_rt, Rows rows, C2<T>* out, long long out_pitch,
                         const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
-  const int Tn = plan.threads, N = plan.n;
+  const int Tn = LOG2N > 0 ? (1 << LOG2N) / SB_FFT_R : plan.threads, N = LOG2N > 0 ? (1 << LOG2N) : plan.n;
+  const int lines_per_block = LOG2N > 0 ? LINES : lines_rt;
   const int l = threadIdx.x / Tn, t = threadIdx.x - l * Tn;
   const int y = blockIdx.x * lines_per_block + l;
   const int z = blockIdx.y, c = blockIdx.z;
@@ -80,7 +81,10 @@ __global__ void __launch_bounds__(512)
   C2<T> v[SB_FFT_R];
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) v[p] = p < IN ? rows.load(c, z, yc, t + p * Tn) : C2<T>{T(0), T(0)};
-  sb_fft_forward<T, false>(v, plan, t, tw, sl);
+  if constexpr (LOG2N > 0)
+    sb_fft_forward_c<T, LOG2N, false, LINES>(v, t, tw, SbFftLineC<T, LOG2N, false, LINES>::line(sm, l));
+  else
+    sb_fft_forward<T, false>(v, plan, t, tw, sl);
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = v[p];
   __syncthreads();
@@ -104,13 +108,14 @@ __global__ void __launch_bounds__(512)
 // N+1 Hermitian bins -> first N reals of the (unnormalised) inverse of length 2N:
 //   Z[k] = (X[k] + conj X[N-k]) + i W_2N^-k (X[k] - conj X[N-k]),  z = ifft_N(Z),
 //   x[2m] = Re z[m], x[2m+1] = Im z[m]   for m < N/2
-template <typename T>
-__global__ void __launch_bounds__(512)
-    sb_fft_x_c2r_kernel(SbFftPlan plan, int lines_per_block, const C2<T>* in, long long in_pitch,
+template <typename T, int LOG2N, int LINES>
+__global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 512)
+    sb_fft_x_c2r_kernel(SbFftPlan plan, int lines_rt, const C2<T>* in, long long in_pitch,
                         FieldRows<T> rows, const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
-  const int Tn = plan.threads, N = plan.n;
+  const int Tn = LOG2N > 0 ? (1 << LOG2N) / SB_FFT_R : plan.threads, N = LOG2N > 0 ? (1 << LOG2N) : plan.n;
+  const int lines_per_block = LOG2N > 0 ? LINES : lines_rt;
   const int l = threadIdx.x / Tn, t = threadIdx.x - l * Tn;
   const int y = blockIdx.x * lines_per_block + l;
   const int z = blockIdx.y, c = blockIdx.z;
@@ -133,7 +138,10 @@ __global__ void __launch_bounds__(512)
     v[p] = C2<T>{s.x - wd.y, s.y + wd.x};
   }
   __syncthreads();
-  sb_fft_inverse<T, false>(v, plan, t, tw, sl);
+  if constexpr (LOG2N > 0)
+    sb_fft_inverse_c<T, LOG2N, false, LINES>(v, t, tw, SbFftLineC<T, LOG2N, false, LINES>::line(sm, l));
+  else
+    sb_fft_inverse<T, false>(v, plan, t, tw, sl);
   if (valid) {
     T* orow = rows.row(c, z, y);
 #pragma unroll
@@ -160,13 +168,15 @@ struct SbGreensTable {
   long long g_pt, g_s1;
 };
 
-template <typename T, int MODE>
-__global__ void __launch_bounds__(512)
-    sb_fft_strided_kernel(SbFftPlan plan, int lb_shift, const C2<T>* in, SbLines lin, C2<T>* out, SbLines lout,
+template <typename T, int MODE, int LOG2N, int LINES>
+__global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 512)
+    sb_fft_strided_kernel(SbFftPlan plan, int lb_shift_rt, const C2<T>* in, SbLines lin, C2<T>* out, SbLines lout,
                           const C2<T>* __restrict__ tw, SbGreensTable<T> gt) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
-  const int Tn = plan.threads, n = plan.n;
+  const int Tn = LOG2N > 0 ? (1 << LOG2N) / SB_FFT_R : plan.threads, n = LOG2N > 0 ? (1 << LOG2N) : plan.n;
+  constexpr int LINES_SHIFT = LINES == 16 ? 4 : LINES == 8 ? 3 : LINES == 4 ? 2 : LINES == 2 ? 1 : 0;
+  const int lb_shift = LOG2N > 0 ? LINES_SHIFT : lb_shift_rt;
   const int l = threadIdx.x & ((1 << lb_shift) - 1), t = threadIdx.x >> lb_shift;
   const int i = (blockIdx.x << lb_shift) + l;
   const int o1 = blockIdx.y, o2 = blockIdx.z;
@@ -189,8 +199,13 @@ __global__ void __launch_bounds__(512)
       }
     }
   }
-  if (MODE != 2) sb_fft_forward<T, true>(v, plan, t, tw, sl);
-  if (MODE == 1) {
+  if constexpr (MODE != 2) {
+    if constexpr (LOG2N > 0)
+      sb_fft_forward_c<T, LOG2N, true, LINES>(v, t, tw, SbFftLineC<T, LOG2N, true, LINES>::line(sm, l));
+    else
+      sb_fft_forward<T, true>(v, plan, t, tw, sl);
+  }
+  if constexpr (MODE == 1) {
     const int h1 = lout.n1 >> 1;
     const int m1 = o1 <= h1 ? o1 : lout.n1 - o1;
     const T* g = gt.g + ((long long)m1 * gt.g_s1 + ic);
@@ -204,7 +219,12 @@ __global__ void __launch_bounds__(512)
       v[p].y *= s;
     }
   }
-  if (MODE == 1 || MODE == 2) sb_fft_inverse<T, true>(v, plan, t, tw, sl);
+  if constexpr (MODE == 1 || MODE == 2) {
+    if constexpr (LOG2N > 0)
+      sb_fft_inverse_c<T, LOG2N, true, LINES>(v, t, tw, SbFftLineC<T, LOG2N, true, LINES>::line(sm, l));
+    else
+      sb_fft_inverse<T, true>(v, plan, t, tw, sl);
+  }
   if (valid) {
     C2<T>* gp = out + (i + o1 * lout.s1 + o2 * lout.s2 + (long long)t * lout.pt);
     const long long gstride = (long long)Tn * lout.pt;
@@ -266,32 +286,93 @@ static int lines_per_block_for(int threads_per_line, size_t elem, bool strided) 
   return lb;
 }
 
-template <typename T, typename Rows, bool PRUNED>
-static int launch_x_r2c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
-                        long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream) {
-  const int lb = lines_per_block_for(plan.threads, sizeof(T), false);
+// lines per block of the compile-time specialised kernels
+template <typename T>
+constexpr int sb_strided_lines(int log2n) { return (sizeof(T) == 4 && log2n <= 10) ? 8 : 4; }
+constexpr int sb_xpass_lines(int log2n) { return log2n <= 7 ? 16 : log2n == 8 ? 8 : log2n == 9 ? 4 : log2n == 10 ? 2 : 1; }
+
+template <typename T, typename Rows, bool PRUNED, int LOG2N>
+static int launch_x_r2c_c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
+                          long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+  constexpr int LINES = LOG2N > 0 ? sb_xpass_lines(LOG2N) : 0;
+  const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), false);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
-  SB_KERNEL_ATTR_SMEM((sb_fft_x_r2c_kernel<T, Rows, PRUNED>), smem);
+  SB_KERNEL_ATTR_SMEM((sb_fft_x_r2c_kernel<T, Rows, PRUNED, LOG2N, LINES>), smem);
   const dim3 grid((unsigned)((ny + lb - 1) / lb), (unsigned)nz, (unsigned)ncomp);
-  SB_LAUNCH_COOP((sb_fft_x_r2c_kernel<T, Rows, PRUNED>), grid, dim3(lb * plan.threads), smem, stream, plan, lb,
-                 rows, out, pitch, tw, wpost);
+  SB_LAUNCH_COOP((sb_fft_x_r2c_kernel<T, Rows, PRUNED, LOG2N, LINES>), grid, dim3(lb * plan.threads), smem,
+                 stream, plan, lb, rows, out, pitch, tw, wpost);
   SB_CHECK_LAUNCH("fft_x_r2c");
   return 0;
 }
+template <typename T, typename Rows, bool PRUNED>
+static int launch_x_r2c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
+                        long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+  if (sizeof(T) == 4 && PRUNED) {
+    switch (plan.log2n) {
+      case 8: return launch_x_r2c_c<T, Rows, PRUNED, 8>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
+      case 9: return launch_x_r2c_c<T, Rows, PRUNED, 9>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
+      case 10: return launch_x_r2c_c<T, Rows, PRUNED, 10>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
+      default: break;
+    }
+  }
+  return launch_x_r2c_c<T, Rows, PRUNED, 0>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
+}
 
-template <typename T, int MODE>
-static int launch_strided(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
-                          const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
-  const int lb = lines_per_block_for(plan.threads, sizeof(T), true);
+template <typename T, int LOG2N>
+static int launch_x_c2r_c(const SbFftPlan& plan, int ny, int nz, int ncomp, const C2<T>* in, long long pitch,
+                          const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+  constexpr int LINES = LOG2N > 0 ? sb_xpass_lines(LOG2N) : 0;
+  const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), false);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
-  SB_KERNEL_ATTR_SMEM((sb_fft_strided_kernel<T, MODE>), smem);
+  SB_KERNEL_ATTR_SMEM((sb_fft_x_c2r_kernel<T, LOG2N, LINES>), smem);
+  const dim3 grid((unsigned)((ny + lb - 1) / lb), (unsigned)nz, (unsigned)ncomp);
+  SB_LAUNCH_COOP((sb_fft_x_c2r_kernel<T, LOG2N, LINES>), grid, dim3(lb * plan.threads), smem, stream, plan, lb,
+                 in, pitch, dst, tw, wpost);
+  SB_CHECK_LAUNCH("fft_x_c2r");
+  return 0;
+}
+template <typename T>
+static int launch_x_c2r(const SbFftPlan& plan, int ny, int nz, int ncomp, const C2<T>* in, long long pitch,
+                        const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+  if (sizeof(T) == 4) {
+    switch (plan.log2n) {
+      case 8: return launch_x_c2r_c<T, 8>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
+      case 9: return launch_x_c2r_c<T, 9>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
+      case 10: return launch_x_c2r_c<T, 10>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
+      default: break;
+    }
+  }
+  return launch_x_c2r_c<T, 0>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
+}
+
+template <typename T, int MODE, int LOG2N>
+static int launch_strided_c(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
+                            const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
+  constexpr int LINES = LOG2N > 0 ? sb_strided_lines<T>(LOG2N) : 0;
+  const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), true);
+  const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
+  SB_KERNEL_ATTR_SMEM((sb_fft_strided_kernel<T, MODE, LOG2N, LINES>), smem);
   int lb_shift = 0;
   while ((1 << lb_shift) < lb) ++lb_shift;
   const dim3 grid((unsigned)((lin.inner + lb - 1) / lb), (unsigned)lin.n1, (unsigned)lin.n2);
-  SB_LAUNCH_COOP((sb_fft_strided_kernel<T, MODE>), grid, dim3(lb * plan.threads), smem, stream, plan, lb_shift,
-                 in, lin, out, lout, tw, gt);
+  SB_LAUNCH_COOP((sb_fft_strided_kernel<T, MODE, LOG2N, LINES>), grid, dim3(lb * plan.threads), smem, stream,
+                 plan, lb_shift, in, lin, out, lout, tw, gt);
   SB_CHECK_LAUNCH("fft_strided");
   return 0;
+}
+template <typename T, int MODE>
+static int launch_strided(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
+                          const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
+  if (sizeof(T) == 4 && MODE != 3) {
+    switch (plan.log2n) {
+      case 8: return launch_strided_c<T, MODE, 8>(plan, in, lin, out, lout, tw, gt, stream);
+      case 9: return launch_strided_c<T, MODE, 9>(plan, in, lin, out, lout, tw, gt, stream);
+      case 10: return launch_strided_c<T, MODE, 10>(plan, in, lin, out, lout, tw, gt, stream);
+      case 11: return launch_strided_c<T, MODE, 11>(plan, in, lin, out, lout, tw, gt, stream);
+      default: break;
+    }
+  }
+  return launch_strided_c<T, MODE, 0>(plan, in, lin, out, lout, tw, gt, stream);
 }
 
 template <typename T>
@@ -383,15 +464,9 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
     SbGreensTable<T> gt{st->G, P, 0};
     if ((e = launch_strided<T, 1>(st->py, st->A, ly, st->A, ly, st->twy, gt, stream))) return e;
   }
-  const int lbx = lines_per_block_for(st->px.threads, sizeof(T), false);
-  const size_t smem = (size_t)lbx * sb_fft_npad(st->px.n) * sizeof(C2<T>);
-  SB_KERNEL_ATTR_SMEM(sb_fft_x_c2r_kernel<T>, smem);
   FieldRows<T> dst{(T*)solution, ny, gs, p->dim, my, mx, vol};
-  SB_LAUNCH_COOP(sb_fft_x_c2r_kernel<T>, dim3((unsigned)((ny + lbx - 1) / lbx), (unsigned)nz, (unsigned)ncomp),
-                 dim3(lbx * st->px.threads), smem, stream, st->px, lbx, (const C2<T>*)st->A, P, dst,
-                 (const C2<T>*)st->twx, (const C2<T>*)st->wpost);
-  SB_CHECK_LAUNCH("fft_x_c2r");
-  return 0;
+  return launch_x_c2r<T>(st->px, ny, nz, ncomp, (const C2<T>*)st->A, P, dst, (const C2<T>*)st->twx,
+                         (const C2<T>*)st->wpost, stream);
 }
 
 template <typename T>

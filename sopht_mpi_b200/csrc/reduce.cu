@@ -120,53 +120,83 @@ extern "C" int sb200_sum_squares(const sb200_grid_t* g, const void* f, int ncomp
 // u = p*curl(psi) on the wrapper's cells, 0 on the physical ring, + U_inf;
 // F = 0; max over interior of sum_c |u_c|  -- one read of psi, one write of u.
 // (reference flow_simulators_mpi_3d.py:388-393, 422-424, 429-442)
+// Each thread owns one (y,x) column and marches over a chunk of z planes: the (y,x) part of
+// the wrapper masks and the addresses are computed once, the z part is uniform per plane.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    sb_velocity_kernel(SbGeom g, T* u, const T* psi, T p, T u0, T u1, T u2, T* forcing, void* max_out) {
+    sb_velocity_kernel(SbGeom g, T* __restrict__ u, const T* __restrict__ psi, T p, T u0, T u1, T u2,
+                       T* __restrict__ forcing, void* max_out, int zchunk) {
   const long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int z = blockIdx.y;
-  const int y = pidx < g.plane ? (int)(pidx / g.mx) : g.my;
-  const int x = pidx < g.plane ? (int)(pidx - (long long)y * g.mx) : g.mx;
-  double v = -1.0e300;
-  if (x < g.mx && y < g.my && z < g.mz) {
-    const long long i = g.idx(z, y, x);
-    const bool ring = g.in_ring(z, y, x);
-    const bool wr = g.written(z, y, x, 1, g.dim == 3);
-    const int nc = g.dim;
-    T c[3] = {0, 0, 0};
-    if (ring || wr) {
-      if (!ring) {
-        if (g.dim == 3) {
-          const long long n = g.vol, sy = g.mx, sz = g.plane;
-          const T* fx = psi;
-          const T* fy = psi + n;
-          const T* fz = psi + 2 * n;
-          c[0] = p * (fz[i + sy] - fz[i - sy] - fy[i + sz] + fy[i - sz]);
-          c[1] = p * (fx[i + sz] - fx[i - sz] - fz[i + 1] + fz[i - 1]);
-          c[2] = p * (fy[i + 1] - fy[i - 1] - fx[i + sy] + fx[i - sy]);
-        } else {
-          c[0] = p * (psi[i + g.mx] - psi[i - g.mx]);
-          c[1] = -p * (psi[i + 1] - psi[i - 1]);
+  const int zb = blockIdx.y * zchunk;
+  const int ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
+  double vmax = -1.0e300;
+  if (pidx < g.plane) {
+    const int y = (int)(pidx / g.mx);
+    const int x = (int)(pidx - (long long)y * g.mx);
+    const int gs = g.gs;
+    const bool xs = (x == gs) || (x == g.mx - gs - 1);
+    const bool xi = x > gs && x < g.mx - gs - 1;
+    const bool ys = (y == gs) || (y == g.my - gs - 1);
+    const bool yi = y > gs && y < g.my - gs - 1;
+    const bool yfull = y >= 1 && y < g.my - 1;
+    const bool d3 = g.dim == 3;
+    // written = (mA && zfull) || (mB && zin) || (mC && zi)   (2D: mA only)
+    const bool mA = d3 ? ((xs && yfull) || (xi && ys)) : ((xs && yfull) || (xi && (ys || yi)));
+    const bool mB = d3 && xi && yi;
+    const bool mC = d3 && yi && x >= 1 && x < g.mx - 1;  // curl's interior call does not slice x
+    const int w = gs + 1;
+    const bool ring_yx = (g.phys[4] && x < w) || (g.phys[5] && x >= g.mx - w) || (g.phys[2] && y < w) ||
+                         (g.phys[3] && y >= g.my - w);
+    const bool int_yx = x >= gs && x < g.mx - gs && y >= gs && y < g.my - gs;
+    const long long n = g.vol, sy = g.mx, sz = g.plane;
+    long long i = (long long)zb * g.plane + pidx;
+    for (int z = zb; z < ze; ++z, i += sz) {
+      const bool zfull = !d3 || (z >= 1 && z < g.mz - 1);
+      const bool zin = z >= gs && z < g.mz - gs;
+      const bool zi = z > gs && z < g.mz - gs - 1;
+      const bool ring = ring_yx || (d3 && ((g.phys[0] && z < w) || (g.phys[1] && z >= g.mz - w)));
+      const bool wr = (mA && zfull) || (mB && zin) || (mC && zi);
+      T c0 = 0, c1 = 0, c2 = 0;
+      if (ring || wr) {
+        if (!ring) {
+          if (d3) {
+            const T* fx = psi;
+            const T* fy = psi + n;
+            const T* fz = psi + 2 * n;
+            c0 = p * (fz[i + sy] - fz[i - sy] - fy[i + sz] + fy[i - sz]);
+            c1 = p * (fx[i + sz] - fx[i - sz] - fz[i + 1] + fz[i - 1]);
+            c2 = p * (fy[i + 1] - fy[i - 1] - fx[i + sy] + fx[i - sy]);
+          } else {
+            c0 = p * (psi[i + sy] - psi[i - sy]);
+            c1 = -p * (psi[i + 1] - psi[i - 1]);
+          }
         }
+      } else {
+        c0 = u[i];
+        c1 = u[i + n];
+        if (d3) c2 = u[i + 2 * n];
       }
-    } else {
-      for (int k = 0; k < nc; ++k) c[k] = u[i + k * g.vol];
+      c0 += u0;
+      c1 += u1;
+      u[i] = c0;
+      u[i + n] = c1;
+      T s = fabs(c0) + fabs(c1);
+      if (d3) {
+        c2 += u2;
+        u[i + 2 * n] = c2;
+        s += fabs(c2);
+      }
+      if (forcing) {
+        forcing[i] = 0;
+        forcing[i + n] = 0;
+        if (d3) forcing[i + 2 * n] = 0;
+      }
+      if (int_yx && (!d3 || zin)) vmax = (double)s > vmax ? (double)s : vmax;
     }
-    c[0] += u0;
-    c[1] += u1;
-    c[2] += u2;
-    T s = 0;
-    for (int k = 0; k < nc; ++k) {
-      u[i + k * g.vol] = c[k];
-      s += fabs(c[k]);
-      if (forcing) forcing[i + k * g.vol] = 0;
-    }
-    if (g.interior(z, y, x)) v = (double)s;
   }
   if (max_out) {
-    v = sb_block_reduce<true>(v);
-    const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
-    if (tid == 0) atomicMax((unsigned long long*)max_out, sb_key_from_double(v));
+    vmax = sb_block_reduce<true>(vmax);
+    if (threadIdx.x == 0) atomicMax((unsigned long long*)max_out, sb_key_from_double(vmax));
   }
 }
 
@@ -184,15 +214,17 @@ extern "C" int sb200_velocity_from_stream_function(const sb200_grid_t* gr, void*
     int e = sb_memset_async(max_out, 0, 8, stream);
     SB_REQUIRE(e == 0, "velocity: memset failed");
   }
+  const int zchunk = g.mz >= 64 ? 16 : (g.mz >= 16 ? 8 : g.mz);
   dim3 block(256);
-  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)g.mz);
+  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)((g.mz + zchunk - 1) / zchunk));
   if (gr->dtype == SB200_F32) {
     SB_LAUNCH_COOP(sb_velocity_kernel<float>, grid, block, 0, stream, g, (float*)velocity,
                    (const float*)stream_func, (float)prefactor, (float)fs[0], (float)fs[1], (float)fs[2],
-                   (float*)forcing, max_out);
+                   (float*)forcing, max_out, zchunk);
   } else {
     SB_LAUNCH_COOP(sb_velocity_kernel<double>, grid, block, 0, stream, g, (double*)velocity,
-                   (const double*)stream_func, prefactor, fs[0], fs[1], fs[2], (double*)forcing, max_out);
+                   (const double*)stream_func, prefactor, fs[0], fs[1], fs[2], (double*)forcing, max_out,
+                   zchunk);
   }
   SB_CHECK_LAUNCH("velocity_from_stream_function");
   if (max_out) {

@@ -57,6 +57,13 @@ struct SbGeom {
     if (dim == 3) r = r || (phys[0] && z < w) || (phys[1] && z >= mz - w);
     return r;
   }
+  // deep interior for support-1 wrappers: written by the interior call and outside every ring
+  SB_HD bool deep(int z, int y, int x) const {
+    bool r = (unsigned)(x - gs - 1) < (unsigned)(mx - 2 * gs - 2) &&
+             (unsigned)(y - gs - 1) < (unsigned)(my - 2 * gs - 2);
+    if (dim == 3) r = r && (unsigned)(z - gs - 1) < (unsigned)(mz - 2 * gs - 2);
+    return r;
+  }
   SB_HD bool interior(int z, int y, int x) const {
     bool r = x >= gs && x < mx - gs && y >= gs && y < my - gs;
     if (dim == 3) r = r && z >= gs && z < mz - gs;

@@ -132,7 +132,7 @@ struct UpdateVorticityOp {
   const T* f;
   T p;
   SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
-    if (!g.written(z, y, x, 1)) return;
+    if (!g.deep(z, y, x) && !g.written(z, y, x, 1)) return;
     const long long i = g.idx(z, y, x);
     if (g.dim == 3) {
       T cx, cy, cz;
@@ -185,11 +185,13 @@ struct DiffusionFluxOp {
   T p;
   SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
     const long long i = g.idx(z, y, x);
-    if (g.in_ring(z, y, x)) {
-      flux[i] = 0;
-      return;
+    if (!g.deep(z, y, x)) {
+      if (g.in_ring(z, y, x)) {
+        flux[i] = 0;
+        return;
+      }
+      if (!g.written(z, y, x, 1)) return;
     }
-    if (!g.written(z, y, x, 1)) return;
     T s = f[i + 1] + f[i - 1] + f[i + g.mx] + f[i - g.mx];
     if (g.dim == 3) {
       s += f[i + g.plane] + f[i - g.plane];
