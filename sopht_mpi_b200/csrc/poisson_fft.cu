@@ -12,6 +12,7 @@
 #include "fft_device.h"
 #include "poisson.h"
 
+#include <cstdlib>
 #include <vector>
 
 #ifndef SB200_EMU
@@ -27,12 +28,28 @@
 #define SB_STREAM_SYNC(stream) (void)0
 #endif
 
-// A batch of lines: line (i, o1, o2) starts at element  i + o1*s1 + o2*s2  and its points are
-// `pt` elements apart.  The grid is (ceil(inner / lines_per_block), n1, n2): no index division.
+// A batch of lines.  Line (i, o1, o2) starts at element
+//     i + (o1 & (2^o1_shift - 1)) * s1 + (o1 >> o1_shift) * s1_hi + o2 * s2
+// and point k = t + p*Tn of it (p = 0..15) lives a further
+//     (p >> qs) * bstride + (t + (p & (2^qs - 1)) * Tn) * pt
+// elements on: with qs = 4 this is the plain "k * pt"; smaller qs splits the line into
+// 16 >> qs blocks of (2^qs * Tn) points that sit `bstride` apart (blocked layouts: TLB-friendly
+// z lines on one GPU, and the per-destination blocks of the slab transposes on several).
+// The grid is (ceil(inner / lines_per_block), n1, n2): no index division.
 struct SbLines {
   int inner, n1, n2;
   long long s1, s2;
   long long pt;
+  int o1_shift = 30;
+  long long s1_hi = 0;
+  int qs = 4;
+  long long bstride = 0;
+  SB_HD long long base(int i, int o1, int o2) const {
+    return i + (long long)(o1 & ((1 << o1_shift) - 1)) * s1 + (long long)(o1 >> o1_shift) * s1_hi + o2 * s2;
+  }
+  SB_HD long long point(int t, int p, int Tn) const {
+    return (long long)(p >> qs) * bstride + (long long)(t + (p & ((1 << qs) - 1)) * Tn) * pt;
+  }
 };
 
 // ------------------------------------------------------------- row sources (x pass)
@@ -157,6 +174,16 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
   }
 }
 
+constexpr int sb_lb_threads(int log2n, int lines) { return log2n > 0 ? lines * ((1 << log2n) / SB_FFT_R) : 512; }
+constexpr int sb_lb_blocks(int log2n, int lines, size_t elem) {
+  return (log2n > 0 && elem == 4) ? 1024 / sb_lb_threads(log2n, lines) : 1;
+}
+
+// the fused forward+Green+inverse kernel needs more live registers: hold it to 768 threads / SM
+constexpr int sb_lb_blocks_conv(int log2n, int lines, size_t elem) {
+  return (log2n > 0 && elem == 4 && sb_lb_threads(log2n, lines) <= 256) ? 768 / sb_lb_threads(log2n, lines) : 1;
+}
+
 // -------------------------------------------------------------- strided line pass
 // MODE 0: forward, pruned input (n/2 points read, n written)            -- y forward
 // MODE 1: forward, x real Green's table, inverse, pruned in and out     -- z (2D: y) fused
@@ -168,8 +195,9 @@ struct SbGreensTable {
   long long g_pt, g_s1;
 };
 
+// specialised float kernels are held to <= 64 registers so that 1024 threads stay resident per SM
 template <typename T, int MODE, int LOG2N, int LINES>
-__global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 512)
+__global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb_blocks_conv(LOG2N, LINES, sizeof(T)) : sb_lb_blocks(LOG2N, LINES, sizeof(T)))
     sb_fft_strided_kernel(SbFftPlan plan, int lb_shift_rt, const C2<T>* in, SbLines lin, C2<T>* out, SbLines lout,
                           const C2<T>* __restrict__ tw, SbGreensTable<T> gt) {
   SB_DYN_SMEM(smem_raw);
@@ -187,17 +215,9 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
   constexpr int OUT = (MODE == 1 || MODE == 2) ? SB_FFT_R / 2 : SB_FFT_R;
   C2<T> v[SB_FFT_R];
   {
-    const C2<T>* gp = in + (ic + o1 * lin.s1 + o2 * lin.s2 + (long long)t * lin.pt);
-    const long long gstride = (long long)Tn * lin.pt;
+    const C2<T>* gp = in + lin.base(ic, o1, o2);
 #pragma unroll
-    for (int p = 0; p < SB_FFT_R; ++p) {
-      if (p < IN) {
-        v[p] = *gp;
-        gp += gstride;
-      } else {
-        v[p] = C2<T>{T(0), T(0)};
-      }
-    }
+    for (int p = 0; p < SB_FFT_R; ++p) v[p] = p < IN ? gp[lin.point(t, p, Tn)] : C2<T>{T(0), T(0)};
   }
   if constexpr (MODE != 2) {
     if constexpr (LOG2N > 0)
@@ -226,13 +246,9 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
       sb_fft_inverse<T, true>(v, plan, t, tw, sl);
   }
   if (valid) {
-    C2<T>* gp = out + (i + o1 * lout.s1 + o2 * lout.s2 + (long long)t * lout.pt);
-    const long long gstride = (long long)Tn * lout.pt;
+    C2<T>* gp = out + lout.base(i, o1, o2);
 #pragma unroll
-    for (int p = 0; p < OUT; ++p) {
-      *gp = v[p];
-      gp += gstride;
-    }
+    for (int p = 0; p < OUT; ++p) gp[lout.point(t, p, Tn)] = v[p];
   }
 }
 
@@ -260,7 +276,7 @@ struct SbFftState {
   T* G = nullptr;      // [nz+1][ny+1][P]  (2D: [ny+1][P])
   long long P = 0;
   size_t bytes = 0;
-  int ncomp_cap = 3;
+  int kb = 0;  // ky block size of the B layout (power of two, multiple of 2ny/16, divides 2ny)
 };
 
 template <typename T>
@@ -386,6 +402,11 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   SB_REQUIRE(nx <= 4096 && ny <= 2048 && nz <= 2048, "fft backend: grid too large for one line per block");
   st->P = nx + 2;
   const long long P = st->P;
+  st->kb = 2 * ny;  // plain layout on one GPU (measured: blocking the ky axis does not pay here)
+  if (const char* env = getenv("SB200_FFT_KB")) {
+    const int v = atoi(env);
+    if (v >= st->py.threads && v <= 2 * ny && (v & (v - 1)) == 0) st->kb = v;
+  }
   st->twx = make_twiddles<T>(nx, nx, (double)nx, stream);
   st->wpost = make_twiddles<T>(nx, nx, 2.0 * nx, stream);
   st->twy = make_twiddles<T>(2 * ny, 2 * ny, 2.0 * ny, stream);
@@ -448,12 +469,21 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
     return e;
   SbGreensTable<T> none{nullptr, 0, 0};
   if (p->dim == 3) {
-    // y forward: A[c][z][y][kx] -> B[c][z][ky][kx]
+    // y forward: A[c][z][y][kx] -> B[c][kyb][z][ky_in][kx]  (ky = kyb*KB + ky_in, see SbLines)
+    const int KB = st->kb, Tny = st->py.threads;
+    int kb_shift = 0, q_shift = 0;
+    while ((1 << kb_shift) < KB) ++kb_shift;
+    while ((Tny << q_shift) < KB) ++q_shift;
+    const long long cstride = 2LL * nz * ny * P;
     SbLines la{nx + 1, nz, ncomp, (long long)ny * P, (long long)nz * ny * P, P};
-    SbLines lb{nx + 1, nz, ncomp, 2LL * ny * P, 2LL * nz * ny * P, P};
+    SbLines lb{nx + 1, nz, ncomp, (long long)KB * P, cstride, P};
+    lb.qs = q_shift;
+    lb.bstride = (long long)nz * KB * P;
     if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
-    // z: forward, x Ghat, inverse, in place on B; lines (kx, ky, c)
-    SbLines lz{nx + 1, 2 * ny, ncomp, P, 2LL * nz * ny * P, 2LL * ny * P};
+    // z: forward, x Ghat, inverse, in place on B; lines (kx, ky, c), points KB*P apart
+    SbLines lz{nx + 1, 2 * ny, ncomp, P, cstride, (long long)KB * P};
+    lz.o1_shift = kb_shift;
+    lz.s1_hi = (long long)nz * KB * P;
     SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P};
     if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
     // y inverse: B -> A
