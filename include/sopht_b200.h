@@ -133,6 +133,20 @@ int sb200_poisson_destroy(sb200_poisson_t* p);
 /* single-rank solve of `ncomp` components: psi interior <- solve(rhs interior) */
 int sb200_poisson_solve(sb200_poisson_t* p, void* solution, const void* rhs, int ncomp, void* stream);
 int64_t sb200_poisson_workspace_bytes(const sb200_poisson_t* p);
+/* z-slab decomposition (nranks = 2, 4 or 8; backend 1): mpi4py-fft's distributed transform
+ * (poisson_solver_3d/fft_mpi_3d.py:27-48) and MPIDomainDoublingCommunicator3D
+ * (UnboundedPoissonSolverMPI3D.py:190-382) become
+ *   slab_forward (local x,y passes -> send_buf, blocked by destination rank)
+ *   all-to-all  send_buf -> recv_buf                       (caller: NCCL)
+ *   slab_spectral (fused z forward x Green x z inverse on recv_buf, in place)
+ *   all-to-all  recv_buf -> send_buf
+ *   slab_backward (local y,x inverse passes -> solution interior)
+ * Both buffers hold sb200_poisson_slab_buffer_bytes(p, ncomp) bytes. */
+int64_t sb200_poisson_slab_buffer_bytes(const sb200_poisson_t* p, int ncomp);
+int sb200_poisson_slab_forward(sb200_poisson_t* p, const void* rhs, int ncomp, void* send_buf, void* stream);
+int sb200_poisson_slab_spectral(sb200_poisson_t* p, void* recv_buf, int ncomp, void* stream);
+int sb200_poisson_slab_backward(sb200_poisson_t* p, void* solution, int ncomp, const void* send_buf,
+                                void* stream);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

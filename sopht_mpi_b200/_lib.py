@@ -75,6 +75,10 @@ PROTOTYPES = {
     "sb200_poisson_solve": (c_int, [_V, _V, _V, c_int, _V]),
     "sb200_poisson_workspace_bytes": (c_int64, [_V]),
     "sb200_poisson_fft_available": (c_int, []),
+    "sb200_poisson_slab_buffer_bytes": (c_int64, [_V, c_int]),
+    "sb200_poisson_slab_forward": (c_int, [_V, _V, c_int, _V, _V]),
+    "sb200_poisson_slab_spectral": (c_int, [_V, _V, c_int, _V]),
+    "sb200_poisson_slab_backward": (c_int, [_V, _V, c_int, _V, _V]),
     "sb200_ib_interact_lag": (c_int, [_G, _P, c_int64, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sb200_ib_spread": (c_int, [_G, _P, c_int64, _V, _V, _V, _V]),
     "sb200_clear_ghost_cells": (c_int, [_G, _V, c_int, _V]),

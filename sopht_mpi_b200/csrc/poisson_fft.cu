@@ -193,6 +193,8 @@ template <typename T>
 struct SbGreensTable {
   const T* g;  // [n_pt_half+1][n1_half+1][pitch] reals (mirror compressed)
   long long g_pt, g_s1;
+  int n1_full = 1;  // full length of the o1 (ky) axis of the table
+  int o1_off = 0;   // global ky of this batch's o1 = 0 (slab decomposition)
 };
 
 // specialised float kernels are held to <= 64 registers so that 1024 threads stay resident per SM
@@ -226,8 +228,8 @@ __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb
       sb_fft_forward<T, true>(v, plan, t, tw, sl);
   }
   if constexpr (MODE == 1) {
-    const int h1 = lout.n1 >> 1;
-    const int m1 = o1 <= h1 ? o1 : lout.n1 - o1;
+    const int g1 = o1 + gt.o1_off;
+    const int m1 = g1 <= (gt.n1_full >> 1) ? g1 : gt.n1_full - g1;
     const T* g = gt.g + ((long long)m1 * gt.g_s1 + ic);
     const int half = n >> 1;
 #pragma unroll
@@ -412,9 +414,17 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   st->twy = make_twiddles<T>(2 * ny, 2 * ny, 2.0 * ny, stream);
   if (p->dim == 3) st->twz = make_twiddles<T>(2 * nz, 2 * nz, 2.0 * nz, stream);
   SB_REQUIRE(st->twx && st->wpost && st->twy && (p->dim == 2 || st->twz), "fft backend: twiddle allocation");
-  const long long nzz = p->dim == 3 ? nz : 1;
+  if (p->nranks > 1) {
+    SB_REQUIRE(p->dim == 3, "fft backend: slab decomposition is implemented for 3D grids");
+    SB_REQUIRE(p->nranks == 2 || p->nranks == 4 || p->nranks == 8,
+               "fft backend: slab decomposition needs 2, 4 or 8 ranks");
+    SB_REQUIRE(nz % p->nranks == 0 && nz / p->nranks >= 2 * p->gs, "fft backend: nz must split into slabs");
+  }
+  // z-slab decomposition: this rank holds nz / nranks planes; B (the y-pass output) then lives in
+  // the caller's exchange buffers
+  const long long nzz = p->dim == 3 ? nz / p->nranks : 1;
   const size_t a_bytes = sizeof(C2<T>) * 3 * nzz * ny * P;
-  const size_t b_bytes = p->dim == 3 ? sizeof(C2<T>) * 3 * nzz * 2 * ny * P : 0;
+  const size_t b_bytes = (p->dim == 3 && p->nranks == 1) ? sizeof(C2<T>) * 3 * nzz * 2 * ny * P : 0;
   const size_t g_bytes = sizeof(T) * (p->dim == 3 ? (nz + 1) : 1) * (ny + 1) * P;
   SB_REQUIRE(SB_DEV_ALLOC(st->A, a_bytes), "fft backend: cannot allocate x-pass buffer");
   if (b_bytes) SB_REQUIRE(SB_DEV_ALLOC(st->B, b_bytes), "fft backend: cannot allocate y-pass buffer");
@@ -484,14 +494,14 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
     SbLines lz{nx + 1, 2 * ny, ncomp, P, cstride, (long long)KB * P};
     lz.o1_shift = kb_shift;
     lz.s1_hi = (long long)nz * KB * P;
-    SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P};
+    SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P, 2 * ny, 0};
     if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
     // y inverse: B -> A
     if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
   } else {
     // 2D: fused forward / multiply / inverse along y, in place on A; lines (kx, -, c)
     SbLines ly{nx + 1, 1, ncomp, 0, (long long)ny * P, P};
-    SbGreensTable<T> gt{st->G, P, 0};
+    SbGreensTable<T> gt{st->G, P, 0, 1, 0};
     if ((e = launch_strided<T, 1>(st->py, st->A, ly, st->A, ly, st->twy, gt, stream))) return e;
   }
   FieldRows<T> dst{(T*)solution, ny, gs, p->dim, my, mx, vol};
@@ -515,8 +525,97 @@ static void fft_destroy_t(sb200_poisson* p) {
 }
 
 int sb_poisson_fft_create(sb200_poisson* p, void* stream) {
-  SB_REQUIRE(p->nranks == 1, "fft backend: distributed handles use the slab entry points");
   SB_DISPATCH_DTYPE(p->dtype, return fft_create_t<T>(p, stream));
+}
+
+// ------------------------------------------------------------------ z-slab entry points
+// rank r of P holds planes [r nz/P, (r+1) nz/P).  forward: x r2c + y forward on the local planes,
+// written as P blocks of ky (one per destination rank): S[kyb][c][zl][ky_in][kx].  After the
+// all-to-all every rank owns all z for its ky block, R[zb][c][zl][ky_in][kx]; spectral runs the
+// fused z pass in place; the second all-to-all returns the blocks; backward = y inverse + x c2r.
+template <typename T>
+static void slab_lines(const sb200_poisson* p, const SbFftState<T>* st, int ncomp, SbLines* la, SbLines* lb,
+                       SbLines* lz) {
+  const int P_ = p->nranks, nzl = p->nz / P_, ny = p->ny, nx = p->nx;
+  const long long P = st->P;
+  const int kyl = 2 * ny / P_;
+  const long long blk = (long long)ncomp * nzl * kyl * P;  // one destination / source block
+  *la = SbLines{nx + 1, nzl, ncomp, (long long)ny * P, (long long)nzl * ny * P, P};
+  *lb = SbLines{nx + 1, nzl, ncomp, (long long)kyl * P, (long long)nzl * kyl * P, P};
+  int q = 0;
+  while ((st->py.threads << q) < kyl) ++q;
+  lb->qs = q;
+  lb->bstride = blk;
+  *lz = SbLines{nx + 1, kyl, ncomp, P, (long long)nzl * kyl * P, (long long)kyl * P};
+  int qz = 0;
+  while ((st->pz.threads << qz) < nzl) ++qz;
+  lz->qs = qz;
+  lz->bstride = blk;
+}
+
+template <typename T>
+static int slab_forward_t(sb200_poisson* p, const void* rhs, int ncomp, void* send, void* stream) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+  const int nzl = p->nz / p->nranks, ny = p->ny, nx = p->nx, gs = p->gs;
+  const long long my = ny + 2 * gs, mx = nx + 2 * gs, vol = (nzl + 2LL * gs) * my * mx;
+  SbLines la, lb, lz;
+  slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
+  int e;
+  FieldRows<T> src{(T*)rhs, ny, gs, 3, my, mx, vol};
+  if ((e = launch_x_r2c<T, FieldRows<T>, true>(st->px, ny, nzl, ncomp, src, st->A, st->P, st->twx, st->wpost,
+                                               stream)))
+    return e;
+  SbGreensTable<T> none{nullptr, 0, 0};
+  return launch_strided<T, 0>(st->py, st->A, la, (C2<T>*)send, lb, st->twy, none, stream);
+}
+template <typename T>
+static int slab_spectral_t(sb200_poisson* p, void* recv, int ncomp, void* stream) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+  SbLines la, lb, lz;
+  slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
+  const int kyl = 2 * p->ny / p->nranks;
+  SbGreensTable<T> gt{st->G, (long long)(p->ny + 1) * st->P, st->P, 2 * p->ny, p->rank * kyl};
+  return launch_strided<T, 1>(st->pz, (const C2<T>*)recv, lz, (C2<T>*)recv, lz, st->twz, gt, stream);
+}
+template <typename T>
+static int slab_backward_t(sb200_poisson* p, void* solution, int ncomp, const void* send, void* stream) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+  const int nzl = p->nz / p->nranks, ny = p->ny, nx = p->nx, gs = p->gs;
+  const long long my = ny + 2 * gs, mx = nx + 2 * gs, vol = (nzl + 2LL * gs) * my * mx;
+  SbLines la, lb, lz;
+  slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
+  SbGreensTable<T> none{nullptr, 0, 0};
+  int e = launch_strided<T, 2>(st->py, (const C2<T>*)send, lb, st->A, la, st->twy, none, stream);
+  if (e) return e;
+  FieldRows<T> dst{(T*)solution, ny, gs, 3, my, mx, vol};
+  return launch_x_c2r<T>(st->px, ny, nzl, ncomp, (const C2<T>*)st->A, st->P, dst, (const C2<T>*)st->twx,
+                         (const C2<T>*)st->wpost, stream);
+}
+
+static int slab_check(const sb200_poisson* p, int ncomp) {
+  SB_REQUIRE(p && p->backend == 1 && p->nranks > 1 && p->backend_state,
+             "poisson slab entry points need a distributed handle of the fft backend");
+  SB_REQUIRE(ncomp >= 1 && ncomp <= 3, "poisson slab: ncomp must be 1..3");
+  return 0;
+}
+extern "C" int64_t sb200_poisson_slab_buffer_bytes(const sb200_poisson_t* p, int ncomp) {
+  if (!p || p->nranks < 1) return 0;
+  const int64_t w = p->dtype == SB200_F32 ? 4 : 8;
+  return 2 * w * ncomp * (int64_t)(p->nz / p->nranks) * 2 * p->ny * (p->nx + 2);
+}
+extern "C" int sb200_poisson_slab_forward(sb200_poisson_t* p, const void* rhs, int ncomp, void* send_buf,
+                                          void* stream) {
+  if (int e = slab_check(p, ncomp)) return e;
+  SB_DISPATCH_DTYPE(p->dtype, return slab_forward_t<T>(p, rhs, ncomp, send_buf, stream));
+}
+extern "C" int sb200_poisson_slab_spectral(sb200_poisson_t* p, void* recv_buf, int ncomp, void* stream) {
+  if (int e = slab_check(p, ncomp)) return e;
+  SB_DISPATCH_DTYPE(p->dtype, return slab_spectral_t<T>(p, recv_buf, ncomp, stream));
+}
+extern "C" int sb200_poisson_slab_backward(sb200_poisson_t* p, void* solution, int ncomp, const void* send_buf,
+                                           void* stream) {
+  if (int e = slab_check(p, ncomp)) return e;
+  SB_DISPATCH_DTYPE(p->dtype, return slab_backward_t<T>(p, solution, ncomp, send_buf, stream));
 }
 int sb_poisson_fft_destroy(sb200_poisson* p) {
   if (p->dtype == SB200_F32) fft_destroy_t<float>(p); else fft_destroy_t<double>(p);

@@ -34,9 +34,14 @@ class _UnboundedPoissonSolver:
             pow2 = all(_is_pow2(int(g)) for g in grid_size)
             big_enough = gs3[2] >= 16 and gs3[1] >= 8 and (dim == 2 or gs3[0] >= 8)
             small_enough = gs3[2] <= 4096 and gs3[1] <= 2048 and gs3[0] <= 2048
-            backend = ("fft" if (pow2 and big_enough and small_enough and mpi_construct.size == 1
+            backend = ("fft" if (pow2 and big_enough and small_enough
                                  and _fft_backend_available(self.lib)) else "cufft")
+        if mpi_construct.size > 1 and (backend != "fft" or dim != 3):
+            raise _lib.SophtB200Error(
+                "the distributed Poisson solve needs the fft backend: 3D power-of-two grids on "
+                "2, 4 or 8 z-slabs")
         self.backend = backend
+        self._slab_bufs = {}
         self._handle = ctypes.c_void_p()
         _lib.check(self.lib, self.lib.sb200_poisson_create(
             ctypes.byref(self._handle), dim, _lib.dtype_code(real_t), gs3[0], gs3[1], gs3[2],
@@ -58,9 +63,31 @@ class _UnboundedPoissonSolver:
     def _solve(self, solution, rhs, ncomp):
         st = Staged(self.device)
         s, r = st(solution, out=True), st(rhs)
-        _lib.check(self.lib, self.lib.sb200_poisson_solve(self._handle, dptr(s), dptr(r), ncomp,
-                                                          current_stream_ptr(self.device)))
+        stream = current_stream_ptr(self.device)
+        if self.mpi_construct.size == 1:
+            _lib.check(self.lib, self.lib.sb200_poisson_solve(self._handle, dptr(s), dptr(r), ncomp, stream))
+        else:
+            self._solve_slabs(s, r, ncomp, stream)
         st.finish()
+
+    def _solve_slabs(self, s, r, ncomp, stream):
+        """z-slab solve: local x/y passes, all-to-all (z <-> ky), fused z pass, all-to-all back,
+        local inverse passes.  The transposes replace mpi4py-fft's and the domain-doubling copies
+        (reference ``UnboundedPoissonSolverMPI3D.py:190-382``, ``fft_mpi_3d.py:27-48``)."""
+        import torch
+        import torch.distributed as dist
+
+        if ncomp not in self._slab_bufs:
+            nbytes = int(self.lib.sb200_poisson_slab_buffer_bytes(self._handle, ncomp))
+            self._slab_bufs[ncomp] = (torch.empty(nbytes // 4, dtype=torch.float32, device=self.device),
+                                      torch.empty(nbytes // 4, dtype=torch.float32, device=self.device))
+        send, recv = self._slab_bufs[ncomp]
+        lib, h = self.lib, self._handle
+        _lib.check(lib, lib.sb200_poisson_slab_forward(h, dptr(r), ncomp, dptr(send), stream))
+        dist.all_to_all_single(recv, send)
+        _lib.check(lib, lib.sb200_poisson_slab_spectral(h, dptr(recv), ncomp, stream))
+        dist.all_to_all_single(send, recv)
+        _lib.check(lib, lib.sb200_poisson_slab_backward(h, dptr(s), ncomp, dptr(send), stream))
 
     def solve(self, solution_field, rhs_field):
         """-del^2(solution_field) = rhs_field on the unbounded domain; padded local
