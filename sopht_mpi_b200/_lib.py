@@ -11,6 +11,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsophtb200.so")
+# developer knob: an alternate build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("SB200_LIB", LIB_PATH)
 
 F32, F64 = 0, 1
 

@@ -23,10 +23,81 @@ SB_HD C2<T> cadd(C2<T> a, C2<T> b) { return C2<T>{a.x + b.x, a.y + b.y}; }
 template <typename T>
 SB_HD C2<T> csub(C2<T> a, C2<T> b) { return C2<T>{a.x - b.x, a.y - b.y}; }
 template <typename T>
+SB_HD C2<T> cscale(C2<T> a, T s) { return C2<T>{a.x * s, a.y * s}; }
+template <typename T>
 SB_HD C2<T> cconj(C2<T> a) { return C2<T>{a.x, -a.y}; }
 // multiply by -i  (forward quarter turn)
 template <typename T>
 SB_HD C2<T> cmul_mi(C2<T> a) { return C2<T>{a.y, -a.x}; }
+
+#if defined(__CUDACC__) && !defined(SB200_EMU)
+// float complex arithmetic on the packed sm_100 FP32 forms (add/sub/mul/fma .f32x2 -> FADD2 /
+// FMUL2 / FFMA2): one issue slot per complex add, two per complex multiply.  ptxas folds the lane
+// swaps, negations and scalar broadcasts below into operand modifiers (.LO_HI, .NP, .F32), so
+// cconj / cmul_mi cost nothing.  FP32 lane throughput is unchanged (tools/ubench/f32x2.cu), the
+// gain is issue slots for the address / shared-memory / load instructions between the butterflies.
+#define SB_PACKED_F32 1
+typedef unsigned long long sb_u64;
+SB_D sb_u64 sb_pk(float lo, float hi) {
+  sb_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+SB_D C2<float> sb_up(sb_u64 v) {
+  C2<float> r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+SB_D sb_u64 sb_add2(sb_u64 a, sb_u64 b) {
+  sb_u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SB_D sb_u64 sb_sub2(sb_u64 a, sb_u64 b) {
+  sb_u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SB_D sb_u64 sb_mul2(sb_u64 a, sb_u64 b) {
+  sb_u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SB_D sb_u64 sb_fma2(sb_u64 a, sb_u64 b, sb_u64 c) {
+  sb_u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+SB_HD C2<float> cadd(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+  return sb_up(sb_add2(sb_pk(a.x, a.y), sb_pk(b.x, b.y)));
+#else
+  return C2<float>{a.x + b.x, a.y + b.y};
+#endif
+}
+SB_HD C2<float> csub(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+  return sb_up(sb_sub2(sb_pk(a.x, a.y), sb_pk(b.x, b.y)));
+#else
+  return C2<float>{a.x - b.x, a.y - b.y};
+#endif
+}
+SB_HD C2<float> cscale(C2<float> a, float s) {
+#ifdef __CUDA_ARCH__
+  return sb_up(sb_mul2(sb_pk(a.x, a.y), sb_pk(s, s)));
+#else
+  return C2<float>{a.x * s, a.y * s};
+#endif
+}
+SB_HD C2<float> cmul(C2<float> a, C2<float> b) {
+#ifdef __CUDA_ARCH__
+  // (ax bx - ay by, ay bx + ax by) = (ax, ay) * (bx, bx) + (ay, ax) * (-by, by)
+  return sb_up(sb_fma2(sb_pk(a.x, a.y), sb_pk(b.x, b.x), sb_mul2(sb_pk(a.y, a.x), sb_pk(-b.y, b.y))));
+#else
+  return C2<float>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+#endif
+}
+#endif
 
 #define SB_FFT_R 16        // points per thread
 #define SB_FFT_MAXSTAGES 4
@@ -85,9 +156,9 @@ SB_D void dft_small(C2<T>* a) {
     dft4(e[0], e[1], e[2], e[3]);
     dft4(o[0], o[1], o[2], o[3]);
     // twiddle W8^k1 on the odd branch
-    o[1] = C2<T>{h * (o[1].x + o[1].y), h * (o[1].y - o[1].x)};
+    o[1] = cscale(cadd(o[1], cmul_mi(o[1])), h);         // (1 - i)/sqrt2
     o[2] = cmul_mi(o[2]);
-    o[3] = C2<T>{h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y)};
+    o[3] = cscale(csub(cmul_mi(o[3]), o[3]), h);         // (-1 - i)/sqrt2
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       a[k] = cadd(e[k], o[k]);
@@ -371,6 +442,12 @@ SB_D void sb_fft_forward_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict_
 
 template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>
 SB_D void sb_fft_inverse_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+#if defined(__CUDA_ARCH__)
+  // launder the table pointer: in the fused forward/inverse kernel the compiler would otherwise keep
+  // the forward transform's twiddles live in registers for re-use here (24 registers that cost a
+  // resident block); re-loading them hits L1
+  asm volatile("" : "+l"(tw));
+#endif
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
   sb_fft_forward_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, tw, sl);

@@ -179,9 +179,13 @@ constexpr int sb_lb_blocks(int log2n, int lines, size_t elem) {
   return (log2n > 0 && elem == 4) ? 1024 / sb_lb_threads(log2n, lines) : 1;
 }
 
-// the fused forward+Green+inverse kernel needs more live registers: hold it to 768 threads / SM
+// the fused forward+Green+inverse kernel: 256-thread blocks (n <= 512) run 3 per SM at <= 80
+// registers, 512-thread blocks (n = 1024) 2 per SM at 64 registers (measured best on B200:
+// profiles/r01_fft_tuning.md)
 constexpr int sb_lb_blocks_conv(int log2n, int lines, size_t elem) {
-  return (log2n > 0 && elem == 4 && sb_lb_threads(log2n, lines) <= 256) ? 768 / sb_lb_threads(log2n, lines) : 1;
+  if (!(log2n > 0 && elem == 4)) return 1;
+  const int nt = sb_lb_threads(log2n, lines);
+  return nt <= 256 ? 768 / nt : nt <= 512 ? 1024 / nt : 1;
 }
 
 // -------------------------------------------------------------- strided line pass
@@ -195,10 +199,33 @@ struct SbGreensTable {
   long long g_pt, g_s1;
   int n1_full = 1;  // full length of the o1 (ky) axis of the table
   int o1_off = 0;   // global ky of this batch's o1 = 0 (slab decomposition)
+  // thread-order copy for the specialised fused z kernel (see sb_greens_thread_order_kernel):
+  // [m1][kx group][t][line][16 bins of thread t], so a thread's 16 factors are 64 contiguous bytes
+  const T* g2 = nullptr;
 };
 
-// specialised float kernels are held to <= 64 registers so that 1024 threads stay resident per SM
-template <typename T, int MODE, int LOG2N, int LINES>
+// 16-byte asynchronous global -> shared copy (LDGSTS.128); the issuing thread reads its own slot
+// back after sb_cp_async_wait_all(), so no barrier is involved
+SB_D void sb_cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef SB200_EMU
+  memcpy(smem_dst, gsrc, 16);
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+#endif
+}
+SB_D void sb_cp_async_wait_all() {
+#ifndef SB200_EMU
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// specialised float kernels are held to <= 64 registers so that 1024 threads stay resident per SM.
+// BLOCKED = false: both line batches use the plain "k * pt" point addressing (qs == 4), so every
+// thread walks its 16 points with one running pointer (64-bit add per point, no multiplies).
+// VARIANT bit 0: blocked point addressing; bit 1: thread-order Green's table (gt.g2)
+template <typename T, int MODE, int LOG2N, int LINES, int VARIANT>
 __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb_blocks_conv(LOG2N, LINES, sizeof(T)) : sb_lb_blocks(LOG2N, LINES, sizeof(T)))
     sb_fft_strided_kernel(SbFftPlan plan, int lb_shift_rt, const C2<T>* in, SbLines lin, C2<T>* out, SbLines lout,
                           const C2<T>* __restrict__ tw, SbGreensTable<T> gt) {
@@ -208,18 +235,50 @@ __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb
   constexpr int LINES_SHIFT = LINES == 16 ? 4 : LINES == 8 ? 3 : LINES == 4 ? 2 : LINES == 2 ? 1 : 0;
   const int lb_shift = LOG2N > 0 ? LINES_SHIFT : lb_shift_rt;
   const int l = threadIdx.x & ((1 << lb_shift) - 1), t = threadIdx.x >> lb_shift;
-  const int i = (blockIdx.x << lb_shift) + l;
-  const int o1 = blockIdx.y, o2 = blockIdx.z;
+  // grid (kx group, o1, o2); the fused kernel with the thread-order table runs (o2, kx group, o1)
+  // so that the components of one (kx, ky) tile are neighbours and share the table rows in L2
+  constexpr bool BLOCKED = (VARIANT & 1) != 0;
+  constexpr bool G2 = (VARIANT & 2) != 0;
+  static_assert(!G2 || (MODE == 1 && LOG2N > 0 && sizeof(T) == 4), "thread-order table: fused float kernel");
+  const int ib = G2 ? blockIdx.y : blockIdx.x;
+  const int i = (ib << lb_shift) + l;
+  const int o1 = G2 ? blockIdx.z : blockIdx.y, o2 = G2 ? blockIdx.x : blockIdx.z;
   const bool valid = i < lin.inner;
   const int ic = valid ? i : lin.inner - 1;
   const SbSmemLine<T, true> sl = sb_smem_line<T, true>(sm, l, lb_shift, sb_fft_npad(n));
+  // staging slots of the Green's factors: chunk k of thread tid at float4 index k * NT + tid
+  float4* gstage = nullptr;
+  if constexpr (G2) {
+    constexpr int NT = LINES * ((1 << LOG2N) / SB_FFT_R);
+    gstage = reinterpret_cast<float4*>(sm + LINES * SbFftC<LOG2N>::npad) + threadIdx.x;
+    const int g1 = o1 + gt.o1_off;
+    const int m1 = g1 <= (gt.n1_full >> 1) ? g1 : gt.n1_full - g1;
+    const float4* src = reinterpret_cast<const float4*>(gt.g2) +
+                        (((long long)m1 * gridDim.y + ib) * NT + threadIdx.x) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sb_cp_async16(gstage + k * NT, src + k);
+  }
   constexpr int IN = (MODE == 0 || MODE == 1) ? SB_FFT_R / 2 : SB_FFT_R;
   constexpr int OUT = (MODE == 1 || MODE == 2) ? SB_FFT_R / 2 : SB_FFT_R;
   C2<T> v[SB_FFT_R];
   {
     const C2<T>* gp = in + lin.base(ic, o1, o2);
+    if constexpr (BLOCKED) {
 #pragma unroll
-    for (int p = 0; p < SB_FFT_R; ++p) v[p] = p < IN ? gp[lin.point(t, p, Tn)] : C2<T>{T(0), T(0)};
+      for (int p = 0; p < SB_FFT_R; ++p) v[p] = p < IN ? gp[lin.point(t, p, Tn)] : C2<T>{T(0), T(0)};
+    } else {
+      const long long sp = (long long)Tn * lin.pt;
+      gp += (long long)t * lin.pt;
+#pragma unroll
+      for (int p = 0; p < SB_FFT_R; ++p) {
+        if (p < IN) {
+          v[p] = *gp;
+          gp += sp;
+        } else {
+          v[p] = C2<T>{T(0), T(0)};
+        }
+      }
+    }
   }
   if constexpr (MODE != 2) {
     if constexpr (LOG2N > 0)
@@ -227,18 +286,32 @@ __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb
     else
       sb_fft_forward<T, true>(v, plan, t, tw, sl);
   }
-  if constexpr (MODE == 1) {
+  if constexpr (G2) {
+    constexpr int NT = LINES * ((1 << LOG2N) / SB_FFT_R);
+    sb_cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 gv = gstage[k * NT];
+      v[4 * k] = cscale(v[4 * k], gv.x);
+      v[4 * k + 1] = cscale(v[4 * k + 1], gv.y);
+      v[4 * k + 2] = cscale(v[4 * k + 2], gv.z);
+      v[4 * k + 3] = cscale(v[4 * k + 3], gv.w);
+    }
+  } else if constexpr (MODE == 1) {
+    // real, mirror-compressed table: bin k = t + p Tn reads row min(k, n - k); for p < 8 that is
+    // k itself (k < n/2), for p >= 8 it is (n - t) - p Tn -> two running pointers, no selects
     const int g1 = o1 + gt.o1_off;
     const int m1 = g1 <= (gt.n1_full >> 1) ? g1 : gt.n1_full - g1;
     const T* g = gt.g + ((long long)m1 * gt.g_s1 + ic);
-    const int half = n >> 1;
+    const long long gs = (long long)Tn * gt.g_pt;
+    const T* ga = g + (long long)t * gt.g_pt;
+    const T* gb = g + (long long)(n - t - (SB_FFT_R / 2) * Tn) * gt.g_pt;
 #pragma unroll
-    for (int p = 0; p < SB_FFT_R; ++p) {
-      const int k = t + p * Tn;
-      const int mk = k <= half ? k : n - k;
-      const T s = g[mk * gt.g_pt];
-      v[p].x *= s;
-      v[p].y *= s;
+    for (int p = 0; p < SB_FFT_R / 2; ++p) {
+      v[p] = cscale(v[p], *ga);
+      v[p + SB_FFT_R / 2] = cscale(v[p + SB_FFT_R / 2], *gb);
+      ga += gs;
+      gb -= gs;
     }
   }
   if constexpr (MODE == 1 || MODE == 2) {
@@ -249,8 +322,18 @@ __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb
   }
   if (valid) {
     C2<T>* gp = out + lout.base(i, o1, o2);
+    if constexpr (BLOCKED) {
 #pragma unroll
-    for (int p = 0; p < OUT; ++p) gp[lout.point(t, p, Tn)] = v[p];
+      for (int p = 0; p < OUT; ++p) gp[lout.point(t, p, Tn)] = v[p];
+    } else {
+      const long long sp = (long long)Tn * lout.pt;
+      gp += (long long)t * lout.pt;
+#pragma unroll
+      for (int p = 0; p < OUT; ++p) {
+        *gp = v[p];
+        gp += sp;
+      }
+    }
   }
 }
 
@@ -268,6 +351,28 @@ struct GreensExtractOp {
   }
 };
 
+// compressed table g[mk][m1][kx] -> thread order g2[m1][ib][t][l][p]  (bin k = t + p Tn of the line
+// kx = ib LINES + l; mk = min(k, n - k)); kx beyond the pitch reads as zero
+template <typename T>
+struct GreensThreadOrderOp {
+  T* g2;
+  const T* g;
+  long long g_pt, g_s1;
+  int n, Tn, lines, nib, pitch;
+  SB_D void operator()(long long idx) const {
+    const int p = (int)(idx & 15);
+    long long r = idx >> 4;
+    const int l = (int)(r % lines);
+    r /= lines;
+    const int t = (int)(r % Tn);
+    r /= Tn;
+    const int ib = (int)(r % nib);
+    const long long m1 = r / nib;
+    const int k = t + p * Tn, mk = k <= (n >> 1) ? k : n - k, kx = ib * lines + l;
+    g2[idx] = kx < pitch ? g[mk * g_pt + m1 * g_s1 + kx] : T(0);
+  }
+};
+
 // --------------------------------------------------------------------- host state
 template <typename T>
 struct SbFftState {
@@ -276,6 +381,7 @@ struct SbFftState {
   C2<T>* A = nullptr;  // [ncomp][nz][ny][P]
   C2<T>* B = nullptr;  // [ncomp][nz][2ny][P]
   T* G = nullptr;      // [nz+1][ny+1][P]  (2D: [ny+1][P])
+  T* G2 = nullptr;     // thread-order copy of G for the specialised fused z kernel (float, 3D)
   long long P = 0;
   size_t bytes = 0;
   int kb = 0;  // ky block size of the B layout (power of two, multiple of 2ny/16, divides 2ny)
@@ -306,7 +412,10 @@ static int lines_per_block_for(int threads_per_line, size_t elem, bool strided) 
 
 // lines per block of the compile-time specialised kernels
 template <typename T>
-constexpr int sb_strided_lines(int log2n) { return (sizeof(T) == 4 && log2n <= 10) ? 8 : 4; }
+constexpr int sb_strided_lines(int log2n, int mode) {
+  (void)mode;
+  return (sizeof(T) == 4 && log2n <= 10) ? 8 : 4;
+}
 constexpr int sb_xpass_lines(int log2n) { return log2n <= 7 ? 16 : log2n == 8 ? 8 : log2n == 9 ? 4 : log2n == 10 ? 2 : 1; }
 
 template <typename T, typename Rows, bool PRUNED, int LOG2N>
@@ -366,15 +475,38 @@ static int launch_x_c2r(const SbFftPlan& plan, int ny, int nz, int ncomp, const 
 template <typename T, int MODE, int LOG2N>
 static int launch_strided_c(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
                             const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
-  constexpr int LINES = LOG2N > 0 ? sb_strided_lines<T>(LOG2N) : 0;
+  constexpr int LINES = LOG2N > 0 ? sb_strided_lines<T>(LOG2N, MODE) : 0;
   const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), true);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
-  SB_KERNEL_ATTR_SMEM((sb_fft_strided_kernel<T, MODE, LOG2N, LINES>), smem);
   int lb_shift = 0;
   while ((1 << lb_shift) < lb) ++lb_shift;
-  const dim3 grid((unsigned)((lin.inner + lb - 1) / lb), (unsigned)lin.n1, (unsigned)lin.n2);
-  SB_LAUNCH_COOP((sb_fft_strided_kernel<T, MODE, LOG2N, LINES>), grid, dim3(lb * plan.threads), smem, stream,
-                 plan, lb_shift, in, lin, out, lout, tw, gt);
+  const unsigned nib = (unsigned)((lin.inner + lb - 1) / lb);
+  const dim3 grid(nib, (unsigned)lin.n1, (unsigned)lin.n2);
+  const bool blocked = !(lin.qs == 4 && lout.qs == 4);
+#define SB_LAUNCH_STRIDED(VARIANT, GRID, SMEM)                                                             \
+  do {                                                                                                     \
+    SB_KERNEL_ATTR_SMEM((sb_fft_strided_kernel<T, MODE, LOG2N, LINES, VARIANT>), SMEM);                    \
+    SB_LAUNCH_COOP((sb_fft_strided_kernel<T, MODE, LOG2N, LINES, VARIANT>), GRID, dim3(lb * plan.threads), \
+                   SMEM, stream, plan, lb_shift, in, lin, out, lout, tw, gt);                              \
+  } while (0)
+  if constexpr (MODE == 1 && LOG2N > 0 && sizeof(T) == 4) {
+    if (gt.g2) {
+      // + 64 bytes per thread of staged Green's factors; grid (component, kx group, o1)
+      const size_t smem2 = smem + (size_t)lb * plan.threads * 64;
+      const dim3 grid2((unsigned)lin.n2, nib, (unsigned)lin.n1);
+      if (blocked)
+        SB_LAUNCH_STRIDED(3, grid2, smem2);
+      else
+        SB_LAUNCH_STRIDED(2, grid2, smem2);
+      SB_CHECK_LAUNCH("fft_strided");
+      return 0;
+    }
+  }
+  if (blocked)
+    SB_LAUNCH_STRIDED(1, grid, smem);
+  else
+    SB_LAUNCH_STRIDED(0, grid, smem);
+#undef SB_LAUNCH_STRIDED
   SB_CHECK_LAUNCH("fft_strided");
   return 0;
 }
@@ -459,6 +591,17 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   const long long hz1 = p->dim == 3 ? nz + 1 : 1;
   e = sb_launch_flat(hz1 * (ny + 1) * P, GreensExtractOp<T>{st->G, full, P, n2y, (long long)ny + 1, (T)scale},
                      stream, "greens_extract");
+  if (!e && p->dim == 3 && sizeof(T) == 4 && st->pz.log2n >= 8 && st->pz.log2n <= 11) {
+    // thread-order copy for the specialised fused z kernel
+    const int lines = sb_strided_lines<T>(st->pz.log2n, 1), Tn = st->pz.threads;
+    const int nib = (nx + 1 + lines - 1) / lines;
+    const long long count = (long long)(ny + 1) * nib * Tn * lines * SB_FFT_R;
+    SB_REQUIRE(SB_DEV_ALLOC(st->G2, sizeof(T) * count), "fft backend: cannot allocate the thread-order table");
+    st->bytes += sizeof(T) * count;
+    e = sb_launch_flat(count, GreensThreadOrderOp<T>{st->G2, st->G, (long long)(ny + 1) * P, P, 2 * nz, Tn, lines,
+                                                     nib, (int)P},
+                       stream, "greens_thread_order");
+  }
   SB_STREAM_SYNC(stream);
   sb_poisson_free_greens_lines(lines_dev);
   SB_DEV_FREE(full);
@@ -495,6 +638,7 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
     lz.o1_shift = kb_shift;
     lz.s1_hi = (long long)nz * KB * P;
     SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P, 2 * ny, 0};
+    gt.g2 = st->G2;
     if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
     // y inverse: B -> A
     if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
@@ -520,6 +664,7 @@ static void fft_destroy_t(sb200_poisson* p) {
   if (st->A) SB_DEV_FREE(st->A);
   if (st->B) SB_DEV_FREE(st->B);
   if (st->G) SB_DEV_FREE(st->G);
+  if (st->G2) SB_DEV_FREE(st->G2);
   delete st;
   p->backend_state = nullptr;
 }
@@ -575,6 +720,7 @@ static int slab_spectral_t(sb200_poisson* p, void* recv, int ncomp, void* stream
   slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
   const int kyl = 2 * p->ny / p->nranks;
   SbGreensTable<T> gt{st->G, (long long)(p->ny + 1) * st->P, st->P, 2 * p->ny, p->rank * kyl};
+  gt.g2 = st->G2;
   return launch_strided<T, 1>(st->pz, (const C2<T>*)recv, lz, (C2<T>*)recv, lz, st->twz, gt, stream);
 }
 template <typename T>
