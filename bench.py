@@ -25,6 +25,10 @@ sys.path.insert(0, ROOT)
 METRIC = "full_timestep_Mcell_updates_per_s"
 UNIT = "Mcell-updates/s"
 FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused z kernel, from the
+# `ncu --set full` captures kept under profiles/ (r01_ncu_step256_summary.txt, r01_ncu_z512_summary.txt)
+NCU_Z_PASS_TRAFFIC_BYTES = {"vortex_ring_256_f32": 1.075759e9 + 0.760783e9,
+                            "vortex_ring_512_f32": 8.638830e9 + 6.416844e9}
 
 WORKLOADS = {
     # name: (grid (z,y,x), flow_type, with immersed body)
@@ -282,18 +286,53 @@ def main():
         stage_ms[label] = a.elapsed_time(b) / reps
 
     dt_fix = sim.compute_stable_timestep(dt_prefac=0.5)
-    timed("poisson_vector_solve", lambda: sim.unbounded_poisson_solver.vector_field_solve(
+    solver = sim.unbounded_poisson_solver
+    timed("poisson_vector_solve", lambda: solver.vector_field_solve(
         solution_vector_field=sim.stream_func_field, rhs_vector_field=sim.vorticity_field))
     timed("full_step", lambda: sim.time_step(dt=dt_fix, free_stream_velocity=u_inf))
     w_bytes = 4
     local_cells = cells / world
-    poisson_bytes = 86 * w_bytes * local_cells
     peak, peak_src = hbm_peak()
-    achieved = poisson_bytes / (stage_ms["poisson_vector_solve"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "unbounded Poisson vector solve (all launches)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": 86 * w_bytes}
+    # ---- roofline of the dominant kernel: the fused z pass of the Poisson solve (forward FFT x Green's
+    # spectrum x inverse FFT, in place).  Its launches are timed live with CUDA events recorded by the
+    # library on the solve's stream (sb200_poisson_set_profiling), averaged over `steps` solves.
+    # ALGORITHMIC bytes per launch: read 4 W + write 4 W per cell and component.
+    roofline = None
+    if solver.backend == "fft":
+        solver.set_profiling(True)
+        acc = {}
+        for _ in range(max(args.steps, 5)):
+            solver.vector_field_solve(solution_vector_field=sim.stream_func_field,
+                                      rhs_vector_field=sim.vorticity_field)
+            for k, v in solver.last_stage_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / max(args.steps, 5)
+        solver.set_profiling(False)
+        stage_ms.update({"poisson_" + k: v for k, v in acc.items()})
+        zk = "z_fused_forward_green_inverse"
+        z_bytes = 8 * w_bytes * 3 * local_cells
+        achieved = z_bytes / (acc[zk] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "sb_fft_strided_kernel<float, MODE 1> (fused z pass of the Poisson "
+                    "vector solve: forward FFT x Green x inverse FFT, in place)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": NCU_Z_PASS_TRAFFIC_BYTES.get(name) if world == 1 else None,
+                    "peak_source": peak_src,
+                    "launch_ms": acc[zk], "algorithmic_bytes_per_launch": z_bytes,
+                    "algorithmic_bytes_per_cell": 8 * w_bytes * 3,
+                    "share_of_step": acc[zk] / stage_ms["full_step"],
+                    "per_gpu": world > 1,
+                    "note": "the kernel is co-limited by FP32 issue (radix-16 butterflies, ~33 lane-ops per "
+                            "complex point and transform) and HBM; see profiles/r01_fft_tuning.md"}
+    nvlink = None
+    if world > 1 and "poisson_all_to_all_z_to_ky" in stage_ms:
+        # each all-to-all moves the y-pass output (2 W per cell-of-the-doubled-y-axis ... complex, 2ny x (nx+2))
+        # of this GPU's planes, minus the block that stays local
+        a2a_bytes = 2 * w_bytes * 3 * (grid[0] / world) * 2 * grid[1] * (grid[2] + 2) * (world - 1) / world
+        nvlink = {"all_to_all_bytes_out_per_gpu": a2a_bytes,
+                  "GBps_out_per_gpu": [a2a_bytes / (stage_ms[k] * 1e-3) / 1e9
+                                       for k in ("poisson_all_to_all_z_to_ky", "poisson_all_to_all_ky_to_z")],
+                  "peak_GBps_per_direction": 900.0}
+    poisson_bytes = 86 * w_bytes * local_cells
+    poisson_gbs = poisson_bytes / (stage_ms["poisson_vector_solve"] * 1e-3) / 1e9
     step_bytes = (107 if flow_type == "navier_stokes_with_forcing" else 101) * w_bytes * local_cells
     step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
 
@@ -343,7 +382,8 @@ def main():
                        "l2": "working set (>= 1.2 GB of fields per step) is far larger than the 126 MB L2",
                        "step_algorithmic_GBps": step_gbs, "step_hbm_frac_of_measured": step_gbs / peak,
                        "step_hbm_frac_of_nominal_8TBps": step_gbs / 8000.0,
-                       "stage_ms": stage_ms},
+                       "poisson_algorithmic_GBps": poisson_gbs, "poisson_hbm_frac_of_measured": poisson_gbs / peak,
+                       "stage_ms": stage_ms, "nvlink": nvlink},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "operator API with host buffers: vorticity H2D from pinned memory, step, "

@@ -147,6 +147,13 @@ int sb200_poisson_slab_forward(sb200_poisson_t* p, const void* rhs, int ncomp, v
 int sb200_poisson_slab_spectral(sb200_poisson_t* p, void* recv_buf, int ncomp, void* stream);
 int sb200_poisson_slab_backward(sb200_poisson_t* p, void* solution, int ncomp, const void* send_buf,
                                 void* stream);
+/* Per-kernel device times of a single-rank solve of the fft backend: with profiling on, CUDA events
+ * are recorded on the solve's stream around its five launches; sb200_poisson_last_stage_ms
+ * synchronises on the last event and writes n <= 5 times in milliseconds,
+ * {x r2c, y forward, fused z (forward x Green x inverse), y inverse, x c2r}.  bench.py uses it to
+ * time the dominant kernel live, inside its timed region. */
+int sb200_poisson_set_profiling(sb200_poisson_t* p, int enable);
+int sb200_poisson_last_stage_ms(sb200_poisson_t* p, float* ms_out, int n);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

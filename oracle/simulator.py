@@ -122,3 +122,85 @@ class FlowSimulatorOracle3D:
             0.9 * self.dx ** 2 / 6 / (self.kinematic_viscosity + tol),
         )
         return dt * dt_prefac
+
+
+class FlowSimulatorOracle2D:
+    """Single-domain restatement of ``UnboundedFlowSimulator2D``'s step order
+    (reference ``flow_simulators_mpi_2d.py:255-328``)."""
+
+    def __init__(self, grid_size, x_range, kinematic_viscosity, CFL=0.1,
+                 flow_type="navier_stokes_with_forcing", real_t=np.float64, ghost_size=2,
+                 penalty_zone_width=2, with_free_stream_flow=False, fft_workers=1):
+        from . import stencils_2d as st2
+        from .poisson import UnboundedPoissonSolverOracle2D
+
+        self.st2 = st2
+        self.grid_size = tuple(grid_size)
+        ny, nx = self.grid_size
+        self.real_t = real_t
+        self.gs = ghost_size
+        self.flow_type = flow_type
+        self.kinematic_viscosity = kinematic_viscosity
+        self.CFL = CFL
+        self.x_range = x_range
+        self.dx = real_t(x_range / nx)
+        self.penalty_zone_width = penalty_zone_width
+        self.with_free_stream_flow = with_free_stream_flow
+        self.time = 0.0
+        gs, dx = ghost_size, self.dx
+
+        def line(n):  # reference :124-133 on a single rank
+            return np.linspace(dx / 2.0 - gs * dx, n * dx - dx / 2.0 + gs * dx, n + 2 * gs).astype(real_t)
+
+        self.local_x, self.local_y = line(nx), line(ny)
+        shape = (ny + 2 * gs, nx + 2 * gs)
+        self.primary_scalar_field = np.zeros(shape, dtype=real_t)
+        self.velocity_field = np.zeros((2,) + shape, dtype=real_t)
+        self.buffer_scalar_field = np.zeros(shape, dtype=real_t)
+        if flow_type in ("navier_stokes", "navier_stokes_with_forcing"):
+            self.vorticity_field = self.primary_scalar_field
+            self.stream_func_field = np.zeros_like(self.vorticity_field)
+            self.poisson = UnboundedPoissonSolverOracle2D(ny, nx, x_range=x_range, real_t=real_t)
+        if flow_type == "navier_stokes_with_forcing":
+            self.eul_grid_forcing_field = np.zeros_like(self.velocity_field)
+
+    def advection_and_diffusion_timestep(self, dt):  # reference :255-266
+        st2 = self.st2
+        st2.advection_timestep_mpi(self.primary_scalar_field, self.buffer_scalar_field, self.velocity_field,
+                                   self.real_t(dt / self.dx), self.gs)
+        st2.diffusion_timestep_mpi(self.primary_scalar_field, self.buffer_scalar_field,
+                                   self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx), self.gs)
+
+    def compute_velocity_from_vorticity(self):  # reference :268-277
+        st2 = self.st2
+        st2.penalise_field_boundary_mpi(self.vorticity_field, self.penalty_zone_width, self.dx,
+                                        self.local_x, self.local_y, self.gs)
+        self.poisson.solve(self.stream_func_field, self.vorticity_field, self.gs)
+        st2.outplane_field_curl_mpi(self.velocity_field, self.stream_func_field,
+                                    self.real_t(0.5 / self.dx), self.gs)
+
+    def navier_stokes_timestep(self, dt, free_stream_velocity):  # reference :279-282
+        self.advection_and_diffusion_timestep(dt)
+        self.compute_velocity_from_vorticity()
+        if self.with_free_stream_flow:
+            for c in range(2):
+                self.velocity_field[c] += self.real_t(free_stream_velocity[c])
+
+    def time_step(self, dt, free_stream_velocity=(0.0, 0.0)):
+        if self.flow_type == "navier_stokes_with_forcing":  # reference :284-293
+            self.st2.update_vorticity_from_velocity_forcing_mpi(
+                self.vorticity_field, self.eul_grid_forcing_field, self.real_t(dt / (2 * self.dx)), self.gs)
+            self.navier_stokes_timestep(dt, free_stream_velocity)
+            self.eul_grid_forcing_field[...] = 0
+        elif self.flow_type == "navier_stokes":
+            self.navier_stokes_timestep(dt, free_stream_velocity)
+        else:
+            self.advection_and_diffusion_timestep(dt)
+        self.time += dt
+
+    def compute_stable_timestep(self, dt_prefac=1, precision="single"):  # reference :295-318
+        gs = self.gs
+        mag = np.sum(np.fabs(self.velocity_field), axis=0)
+        dt = min(self.CFL * self.dx / (np.amax(mag[gs:-gs, gs:-gs]) + get_test_tol(precision)),
+                 0.9 * self.dx ** 2 / 4 / self.kinematic_viscosity)
+        return dt * dt_prefac

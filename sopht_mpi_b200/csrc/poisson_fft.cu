@@ -385,6 +385,18 @@ struct SbFftState {
   long long P = 0;
   size_t bytes = 0;
   int kb = 0;  // ky block size of the B layout (power of two, multiple of 2ny/16, divides 2ny)
+  // optional per-launch timing (sb200_poisson_set_profiling): events around the five launches
+  bool profile = false, have_times = false;
+#ifndef SB200_EMU
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+#endif
+  void mark(int i, void* stream) {
+#ifndef SB200_EMU
+    if (profile) cudaEventRecord(ev[i], (cudaStream_t)stream);
+#else
+    (void)i; (void)stream;
+#endif
+  }
 };
 
 template <typename T>
@@ -618,8 +630,10 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
   const long long vol = (p->dim == 3 ? nz + 2LL * gs : 1) * my * mx;
   int e;
   FieldRows<T> src{(T*)rhs, ny, gs, p->dim, my, mx, vol};
+  st->mark(0, stream);
   if ((e = launch_x_r2c<T, FieldRows<T>, true>(st->px, ny, nz, ncomp, src, st->A, P, st->twx, st->wpost, stream)))
     return e;
+  st->mark(1, stream);
   SbGreensTable<T> none{nullptr, 0, 0};
   if (p->dim == 3) {
     // y forward: A[c][z][y][kx] -> B[c][kyb][z][ky_in][kx]  (ky = kyb*KB + ky_in, see SbLines)
@@ -633,6 +647,7 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
     lb.qs = q_shift;
     lb.bstride = (long long)nz * KB * P;
     if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
+    st->mark(2, stream);
     // z: forward, x Ghat, inverse, in place on B; lines (kx, ky, c), points KB*P apart
     SbLines lz{nx + 1, 2 * ny, ncomp, P, cstride, (long long)KB * P};
     lz.o1_shift = kb_shift;
@@ -640,17 +655,62 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
     SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P, 2 * ny, 0};
     gt.g2 = st->G2;
     if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
+    st->mark(3, stream);
     // y inverse: B -> A
     if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
+    st->mark(4, stream);
   } else {
+    st->mark(2, stream);
     // 2D: fused forward / multiply / inverse along y, in place on A; lines (kx, -, c)
     SbLines ly{nx + 1, 1, ncomp, 0, (long long)ny * P, P};
     SbGreensTable<T> gt{st->G, P, 0, 1, 0};
     if ((e = launch_strided<T, 1>(st->py, st->A, ly, st->A, ly, st->twy, gt, stream))) return e;
+    st->mark(3, stream);
+    st->mark(4, stream);
   }
   FieldRows<T> dst{(T*)solution, ny, gs, p->dim, my, mx, vol};
-  return launch_x_c2r<T>(st->px, ny, nz, ncomp, (const C2<T>*)st->A, P, dst, (const C2<T>*)st->twx,
-                         (const C2<T>*)st->wpost, stream);
+  e = launch_x_c2r<T>(st->px, ny, nz, ncomp, (const C2<T>*)st->A, P, dst, (const C2<T>*)st->twx,
+                      (const C2<T>*)st->wpost, stream);
+  st->mark(5, stream);
+  st->have_times = st->profile && e == 0;
+  return e;
+}
+
+template <typename T>
+static int fft_set_profiling_t(sb200_poisson* p, int enable) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+#ifndef SB200_EMU
+  if (enable && !st->ev[0])
+    for (auto& ev : st->ev) SB_REQUIRE(cudaEventCreate(&ev) == cudaSuccess, "poisson profiling: cudaEventCreate");
+#endif
+  st->profile = enable != 0;
+  st->have_times = false;
+  return 0;
+}
+template <typename T>
+static int fft_last_stage_ms_t(sb200_poisson* p, float* ms_out, int n) {
+  auto* st = (SbFftState<T>*)p->backend_state;
+  SB_REQUIRE(st->have_times, "poisson profiling: no profiled solve yet");
+  for (int i = 0; i < n && i < 5; ++i) {
+#ifndef SB200_EMU
+    if (i == 0) SB_REQUIRE(cudaEventSynchronize(st->ev[5]) == cudaSuccess, "poisson profiling: event sync");
+    SB_REQUIRE(cudaEventElapsedTime(&ms_out[i], st->ev[i], st->ev[i + 1]) == cudaSuccess,
+               "poisson profiling: elapsed time");
+#else
+    ms_out[i] = 0.f;
+#endif
+  }
+  return 0;
+}
+extern "C" int sb200_poisson_set_profiling(sb200_poisson_t* p, int enable) {
+  SB_REQUIRE(p && p->backend == 1 && p->backend_state && p->nranks == 1,
+             "poisson profiling needs a single-rank handle of the fft backend");
+  SB_DISPATCH_DTYPE(p->dtype, return fft_set_profiling_t<T>(p, enable));
+}
+extern "C" int sb200_poisson_last_stage_ms(sb200_poisson_t* p, float* ms_out, int n) {
+  SB_REQUIRE(p && p->backend == 1 && p->backend_state && ms_out && n >= 1,
+             "poisson profiling needs a handle of the fft backend");
+  SB_DISPATCH_DTYPE(p->dtype, return fft_last_stage_ms_t<T>(p, ms_out, n));
 }
 
 template <typename T>
@@ -665,6 +725,10 @@ static void fft_destroy_t(sb200_poisson* p) {
   if (st->B) SB_DEV_FREE(st->B);
   if (st->G) SB_DEV_FREE(st->G);
   if (st->G2) SB_DEV_FREE(st->G2);
+#ifndef SB200_EMU
+  for (auto& ev : st->ev)
+    if (ev) cudaEventDestroy(ev);
+#endif
   delete st;
   p->backend_state = nullptr;
 }

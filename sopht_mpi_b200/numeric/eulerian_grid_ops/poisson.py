@@ -60,6 +60,28 @@ class _UnboundedPoissonSolver:
     def workspace_bytes(self):
         return int(self.lib.sb200_poisson_workspace_bytes(self._handle))
 
+    STAGE_NAMES = ("x_r2c", "y_forward", "z_fused_forward_green_inverse", "y_inverse", "x_c2r")
+
+    SLAB_STAGE_NAMES = ("local_x_r2c_y_forward", "all_to_all_z_to_ky", "z_fused_forward_green_inverse",
+                        "all_to_all_ky_to_z", "local_y_inverse_x_c2r")
+
+    def set_profiling(self, enable=True):
+        """Record CUDA events around the launches of a solve (single rank: the five kernels, inside
+        the library; z-slabs: the three local stages and the two all-to-alls, on the torch stream)."""
+        if self.mpi_construct.size == 1:
+            _lib.check(self.lib, self.lib.sb200_poisson_set_profiling(self._handle, int(bool(enable))))
+        self._slab_events = [] if enable else None
+
+    def last_stage_ms(self):
+        """Device time (ms) of each stage of the last profiled solve."""
+        if self.mpi_construct.size == 1:
+            out = (ctypes.c_float * 5)()
+            _lib.check(self.lib, self.lib.sb200_poisson_last_stage_ms(self._handle, out, 5))
+            return dict(zip(self.STAGE_NAMES, (float(v) for v in out)))
+        ev = self._slab_events
+        ev[-1].synchronize()
+        return {name: ev[i].elapsed_time(ev[i + 1]) for i, name in enumerate(self.SLAB_STAGE_NAMES)}
+
     def _solve(self, solution, rhs, ncomp):
         st = Staged(self.device)
         s, r = st(solution, out=True), st(rhs)
@@ -83,11 +105,27 @@ class _UnboundedPoissonSolver:
                                       torch.empty(nbytes // 4, dtype=torch.float32, device=self.device))
         send, recv = self._slab_bufs[ncomp]
         lib, h = self.lib, self._handle
+        events = getattr(self, "_slab_events", None)
+        if events is not None:
+            events.clear()
+
+        def mark():
+            if events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                events.append(ev)
+
+        mark()
         _lib.check(lib, lib.sb200_poisson_slab_forward(h, dptr(r), ncomp, dptr(send), stream))
+        mark()
         dist.all_to_all_single(recv, send)
+        mark()
         _lib.check(lib, lib.sb200_poisson_slab_spectral(h, dptr(recv), ncomp, stream))
+        mark()
         dist.all_to_all_single(send, recv)
+        mark()
         _lib.check(lib, lib.sb200_poisson_slab_backward(h, dptr(s), ncomp, dptr(send), stream))
+        mark()
 
     def solve(self, solution_field, rhs_field):
         """-del^2(solution_field) = rhs_field on the unbounded domain; padded local

@@ -173,6 +173,56 @@ def test_2d_operators(real_t):
     assert _rel(w[inner], ref) < _tol(real_t)
 
 
+@pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("phys", [(1, 1, 1, 1), (0, 1, 1, 1), (0, 0, 1, 1)], ids=["single", "first_slab", "inner_slab"])
+def test_2d_operators_against_the_2d_wrapper_oracle(real_t, phys):
+    """Every 2D operator of config 1 against oracle/stencils_2d.py (five wrapper regions, ring
+    zeroing, x-then-y penalisation), on single-domain and y-slab face patterns."""
+    from oracle import stencils_2d as st2
+    from sopht_mpi_b200.numeric.eulerian_grid_ops.ops import _penalise_factor_table
+
+    rng = np.random.default_rng(11)
+    n, gs = (12, 17), 2
+    shape = tuple(v + 2 * gs for v in n)
+    g = _lib.make_grid(2, real_t, gs, n, phys)
+    tol = _tol(real_t)
+    w = rng.uniform(size=shape).astype(real_t)
+    f = rng.uniform(size=(2,) + shape).astype(real_t)
+    vel = (rng.uniform(size=(2,) + shape) - 0.5).astype(real_t)
+    # forcing update
+    a0, a1 = w.copy(), w.copy()
+    st2.update_vorticity_from_velocity_forcing_mpi(a0, f, 0.37, gs)
+    call("sb200_update_vorticity_from_velocity_forcing", ctypes.byref(g), ptr(a1), ptr(f), 0.37, None)
+    assert _rel(a1, a0) < tol
+    # out-of-plane curl + ring
+    c0 = rng.uniform(size=(2,) + shape).astype(real_t)
+    c1 = c0.copy()
+    st2.outplane_field_curl_mpi(c0, w, 0.8, gs, phys)
+    call("sb200_curl", ctypes.byref(g), ptr(c1), ptr(w), 0.8, None)
+    assert _rel(c1, c0) < tol
+    # diffusion time step (flux buffer holds garbage on entry)
+    a0, a1 = w.copy(), w.copy()
+    fl0, fl1 = np.ones(shape, real_t), np.ones(shape, real_t)
+    st2.diffusion_timestep_mpi(a0, fl0, 0.1, gs, phys)
+    call("sb200_diffusion_timestep", ctypes.byref(g), ptr(a1), 1, ptr(fl1), 0.1, None)
+    assert _rel(a1, a0) < tol
+    # ENO3 advection time step: compare where every operand is defined ([2:-2], like the reference tests)
+    a0, a1 = w.copy(), w.copy()
+    fl0, fl1 = np.ones(shape, real_t), np.ones(shape, real_t)
+    st2.advection_timestep_mpi(a0, fl0, vel, 0.2, gs)
+    call("sb200_advection_timestep_eno3", ctypes.byref(g), ptr(a1), 1, ptr(fl1), ptr(vel), 0.2, None)
+    assert _rel(a1[2:-2, 2:-2], a0[2:-2, 2:-2]) < tol
+    # penalisation is bit exact (tabulated sine factors)
+    dx = real_t(1.0 / n[1])
+    xg = ((np.arange(shape[1]) - gs + 0.5) * dx).astype(real_t)
+    yg = ((np.arange(shape[0]) - gs + 0.5) * dx).astype(real_t)
+    a0, a1 = w.copy(), w.copy()
+    st2.penalise_field_boundary_mpi(a0, 3, dx, xg, yg, gs, phys)
+    tab = _penalise_factor_table(real_t, 3, dx, gs, [yg, xg])
+    call("sb200_penalise_field_boundary", ctypes.byref(g), ptr(a1), 1, 3, ptr(tab), None)
+    assert np.array_equal(a0, a1)
+
+
 IB_FILES = sorted(glob.glob(os.path.join(GOLDEN, "ib_*.npz")))
 
 

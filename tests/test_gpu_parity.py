@@ -337,6 +337,95 @@ def test_simulator_steps_against_oracle(cuda, real_t, steps, flow_type, fused):
     assert sim.time == pytest.approx(ora.time)
 
 
+@pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
+def test_simulator_2d_cylinder_against_oracle(cuda, real_t):
+    """BASELINE config 1 (2D flow past a cylinder: navier_stokes_with_forcing + free stream +
+    virtual boundary forcing on 60 points), at 64 x 128, against the composed CPU oracle."""
+    from oracle.simulator import FlowSimulatorOracle2D
+    from sopht_mpi_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcingMPI
+    from sopht_mpi_b200.simulator import UnboundedFlowSimulator2D
+
+    n = (64, 128)
+    radius, u_free = 0.06, 1.0
+    nu = radius * u_free / 200.0
+    kw = dict(grid_size=n, x_range=1.0, kinematic_viscosity=nu, flow_type="navier_stokes_with_forcing",
+              real_t=real_t, with_free_stream_flow=True)
+    sim = UnboundedFlowSimulator2D(**kw)
+    ora = FlowSimulatorOracle2D(**kw)
+    gs = sim.ghost_size
+    assert sim.position_field.shape == (2,) + tuple(v + 2 * gs for v in n)
+    assert np.array_equal(sim.position_field[0][0], ora.local_x)
+    theta = 2 * np.pi * np.arange(60) / 60
+    pos = np.stack([2.5 * radius + radius * np.cos(theta), 0.25 + radius * np.sin(theta)])
+    vel = np.zeros_like(pos)
+    max_lag_dx = 2 * np.pi * radius / 60
+    k, c = -5e4 * max_lag_dx, -20 * max_lag_dx
+    vbf = VirtualBoundaryForcingMPI(mpi_construct=sim.mpi_construct, ghost_size=gs,
+                                    virtual_boundary_stiffness_coeff=k, virtual_boundary_damping_coeff=c,
+                                    grid_dim=2, dx=sim.dx, global_lag_grid_position_field=pos)
+    vbf_o = ib_oracle.VirtualBoundaryForcingOracle(k, c, 2, ora.dx, real_t, np.float64, gs)
+    u_inf = [u_free, 0.0]
+    for c_ in range(2):
+        ora.velocity_field[c_] += real_t(u_inf[c_])
+    sim.velocity_field[...] = ora.velocity_field
+    for _ in range(6):
+        dt = ora.compute_stable_timestep()
+        assert abs(sim.compute_stable_timestep() - dt) <= 1e-6 * dt
+        vbf_o.compute_interaction_force_on_eul_and_lag_grid(ora.eul_grid_forcing_field, ora.velocity_field,
+                                                            pos, vel)
+        vbf.compute_interaction_forcing(local_eul_grid_forcing_field=sim.eul_grid_forcing_field,
+                                        local_eul_grid_velocity_field=sim.velocity_field,
+                                        global_lag_grid_position_field=pos,
+                                        global_lag_grid_velocity_field=vel)
+        vbf_o.time_step(dt)
+        vbf.time_step(dt=dt)
+        ora.time_step(dt, free_stream_velocity=u_inf)
+        sim.time_step(dt=dt, free_stream_velocity=u_inf)
+    tol = TOL[real_t]
+    assert np.abs(ora.vorticity_field).max() > 1.0  # the body did shed vorticity
+    assert _rel(sim.vorticity_field, ora.vorticity_field) <= tol
+    assert _rel(sim.velocity_field, ora.velocity_field) <= tol
+    assert _rel(sim.stream_func_field, ora.stream_func_field) <= tol
+    assert _rel(vbf.global_lag_grid_forcing_field, vbf_o.forcing) <= 10 * tol
+    assert abs(sim.get_max_vorticity() - ora.vorticity_field[gs:-gs, gs:-gs].max()) <= 50 * tol * np.abs(
+        ora.vorticity_field).max()
+
+
+@pytest.mark.parametrize("flow_type", ["passive_scalar", "navier_stokes"])
+def test_simulator_2d_other_flow_types(cuda, flow_type):
+    from oracle.simulator import FlowSimulatorOracle2D
+    from sopht_mpi_b200.simulator import UnboundedFlowSimulator2D
+
+    real_t, n = np.float64, (32, 64)
+    kw = dict(grid_size=n, x_range=1.0, kinematic_viscosity=2e-3, flow_type=flow_type, real_t=real_t)
+    sim, ora = UnboundedFlowSimulator2D(**kw), FlowSimulatorOracle2D(**kw)
+    yy, xx = np.meshgrid(ora.local_y, ora.local_x, indexing="ij")
+    q = np.exp(-((xx - 0.5) ** 2 + (yy - 0.25) ** 2) / 0.004).astype(real_t)
+    ora.primary_scalar_field[...] = q
+    sim.primary_scalar_field[...] = q
+    if flow_type == "passive_scalar":
+        vel = np.stack([-(yy - 0.25), xx - 0.5]).astype(real_t)
+        ora.velocity_field[...] = vel
+        sim.velocity_field[...] = vel
+    else:
+        ora.compute_velocity_from_vorticity()
+        sim.compute_velocity_from_vorticity()
+    for _ in range(4):
+        dt = ora.compute_stable_timestep()
+        assert abs(sim.compute_stable_timestep() - dt) <= 1e-12
+        ora.time_step(dt)
+        sim.time_step(dt)
+    gs = 2
+    assert _rel(np.asarray(sim.primary_scalar_field)[gs:-gs, gs:-gs],
+                ora.primary_scalar_field[gs:-gs, gs:-gs]) <= 1e-10
+    assert _rel(sim.velocity_field, ora.velocity_field) <= 1e-10
+    with pytest.raises(ValueError):
+        UnboundedFlowSimulator2D(grid_size=n, x_range=1.0, kinematic_viscosity=1e-3, flow_type="bogus")
+    with pytest.raises(ValueError):
+        UnboundedFlowSimulator2D(grid_size=n, x_range=1.0, kinematic_viscosity=1e-3,
+                                 flow_type="passive_scalar", with_free_stream_flow=True)
+
+
 @pytest.mark.parametrize("flow_type", ["passive_scalar", "passive_vector"])
 def test_passive_flows_against_oracle(cuda, flow_type):
     from sopht_mpi_b200.simulator import UnboundedFlowSimulator3D
