@@ -19,6 +19,9 @@ import time
 
 import numpy as np
 
+# stdout carries ONE JSON line: NCCL's banner / warnings go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -203,7 +206,13 @@ def main():
     grid, flow_type, with_body = WORKLOADS[name]
     grid = list(grid)
     if args.scaling == "weak" and world > 1:
-        grid[0] *= world  # each GPU keeps the single-GPU slab: z grows with N
+        # fixed cells per GPU: the box doubles along z, then y, then x (256^3 -> 512x256x256 -> 512x512x256
+        # -> 512^3 on 1/2/4/8 GPUs, BASELINE configs[4]); the decomposition stays z-slabs
+        f, axis = world, 0
+        while f > 1:
+            grid[axis % 3] *= 2
+            f //= 2
+            axis += 1
     real_t = np.float32
     nu = 1.0 / 1000.0  # Re_Gamma = 1000
     sim = UnboundedFlowSimulator3D(
@@ -213,7 +222,10 @@ def main():
     gs = sim.ghost_size
     x = sim.local_x[None, None, :].astype(np.float64)
     y = sim.local_y[None, :, None].astype(np.float64)
-    z = sim.local_z[:, None, None].astype(np.float64) / (grid[0] / grid[2])  # keep the ring in the box
+    # keep the ring inside the (possibly non-cubic) box: scale every axis to the unit cube
+    x = x / sim.x_range
+    y = y / sim.y_range
+    z = sim.local_z[:, None, None].astype(np.float64) / sim.z_range
     w0 = vortex_ring(x, y, z, real_t)
     host_w = torch.from_numpy(w0).pin_memory()
     sim.vorticity_field[...] = host_w.to(device)
@@ -369,7 +381,8 @@ def main():
                         "sample": "oracle/ restatement of the reference CPU path (numpy + scipy.fft, "
                                   f"workers={cores}) on a 128^3 float32 sub-sample, 3 steps"}
 
-    launches_per_step = getattr(sim, "launches_per_step", None)
+    # every rank runs the counted step (it contains collectives)
+    launches_per_step = count_launches(sim, interactor, u_inf)
     if rank == 0:
         line = {
             "metric": METRIC, "value": cells / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
@@ -388,7 +401,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "operator API with host buffers: vorticity H2D from pinned memory, step, "
                             "vorticity+velocity D2H, every step"},
-            "gpu_launches": count_launches(sim, interactor, u_inf) * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }

@@ -41,7 +41,8 @@ class _UnboundedPoissonSolver:
                 "the distributed Poisson solve needs the fft backend: 3D power-of-two grids on "
                 "2, 4 or 8 z-slabs")
         self.backend = backend
-        self._slab_bufs = {}
+        self._slab_bufs = []
+        self._slab_events = None
         self._handle = ctypes.c_void_p()
         _lib.check(self.lib, self.lib.sb200_poisson_create(
             ctypes.byref(self._handle), dim, _lib.dtype_code(real_t), gs3[0], gs3[1], gs3[2],
@@ -95,37 +96,92 @@ class _UnboundedPoissonSolver:
     def _solve_slabs(self, s, r, ncomp, stream):
         """z-slab solve: local x/y passes, all-to-all (z <-> ky), fused z pass, all-to-all back,
         local inverse passes.  The transposes replace mpi4py-fft's and the domain-doubling copies
-        (reference ``UnboundedPoissonSolverMPI3D.py:190-382``, ``fft_mpi_3d.py:27-48``)."""
+        (reference ``UnboundedPoissonSolverMPI3D.py:190-382``, ``fft_mpi_3d.py:27-48``).
+
+        The components are software-pipelined: each has its own pair of exchange buffers, the
+        kernels run on the caller's stream and the NCCL all-to-alls on a second stream, so the
+        exchange of component c overlaps the transforms of component c +- 1 (events order them).
+        With profiling on, the stages run back to back instead so that each can be timed."""
         import torch
         import torch.distributed as dist
 
-        if ncomp not in self._slab_bufs:
-            nbytes = int(self.lib.sb200_poisson_slab_buffer_bytes(self._handle, ncomp))
-            self._slab_bufs[ncomp] = (torch.empty(nbytes // 4, dtype=torch.float32, device=self.device),
-                                      torch.empty(nbytes // 4, dtype=torch.float32, device=self.device))
-        send, recv = self._slab_bufs[ncomp]
         lib, h = self.lib, self._handle
+        if not self._slab_bufs:
+            nfloat = int(lib.sb200_poisson_slab_buffer_bytes(h, 1)) // 4
+            self._slab_bufs = [(torch.empty(nfloat, dtype=torch.float32, device=self.device),
+                                torch.empty(nfloat, dtype=torch.float32, device=self.device))
+                               for _ in range(3)]
+            # high priority: the NCCL kernels must get SMs while a transform kernel still has blocks queued
+            self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        main = torch.cuda.current_stream(self.device)
+        comm = self._comm_stream
+        vol = r.numel() // ncomp if r.dim() == 4 else r.numel()
+        esize = r.element_size()
+        rp, sp = dptr(r), dptr(s)
+
+        def comp_ptr(base, c):
+            return ctypes.c_void_p(base.value + c * vol * esize)
+
         events = getattr(self, "_slab_events", None)
-        if events is not None:
+        if events is not None:  # serial, timed stages (profiling)
             events.clear()
 
-        def mark():
-            if events is not None:
+            def mark():
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 events.append(ev)
 
-        mark()
-        _lib.check(lib, lib.sb200_poisson_slab_forward(h, dptr(r), ncomp, dptr(send), stream))
-        mark()
-        dist.all_to_all_single(recv, send)
-        mark()
-        _lib.check(lib, lib.sb200_poisson_slab_spectral(h, dptr(recv), ncomp, stream))
-        mark()
-        dist.all_to_all_single(send, recv)
-        mark()
-        _lib.check(lib, lib.sb200_poisson_slab_backward(h, dptr(s), ncomp, dptr(send), stream))
-        mark()
+            mark()
+            for c in range(ncomp):
+                _lib.check(lib, lib.sb200_poisson_slab_forward(h, comp_ptr(rp, c), 1, dptr(self._slab_bufs[c][0]),
+                                                               stream))
+            mark()
+            for c in range(ncomp):
+                dist.all_to_all_single(self._slab_bufs[c][1], self._slab_bufs[c][0])
+            mark()
+            for c in range(ncomp):
+                _lib.check(lib, lib.sb200_poisson_slab_spectral(h, dptr(self._slab_bufs[c][1]), 1, stream))
+            mark()
+            for c in range(ncomp):
+                dist.all_to_all_single(self._slab_bufs[c][0], self._slab_bufs[c][1])
+            mark()
+            for c in range(ncomp):
+                _lib.check(lib, lib.sb200_poisson_slab_backward(h, comp_ptr(sp, c), 1,
+                                                                dptr(self._slab_bufs[c][0]), stream))
+            mark()
+            return
+
+        def after(ev_stream):
+            ev = torch.cuda.Event()
+            ev.record(ev_stream)
+            return ev
+
+        # the exchange buffers may still be in use by the previous solve's last transfers
+        comm.wait_stream(main)
+        fwd, a2a1, spec, a2a2 = [], [], [], []
+        for c in range(ncomp):
+            send, _ = self._slab_bufs[c]
+            _lib.check(lib, lib.sb200_poisson_slab_forward(h, comp_ptr(rp, c), 1, dptr(send), stream))
+            fwd.append(after(main))
+        for c in range(ncomp):
+            send, recv = self._slab_bufs[c]
+            with torch.cuda.stream(comm):
+                comm.wait_event(fwd[c])
+                dist.all_to_all_single(recv, send)
+                a2a1.append(after(comm))
+        for c in range(ncomp):
+            send, recv = self._slab_bufs[c]
+            main.wait_event(a2a1[c])
+            _lib.check(lib, lib.sb200_poisson_slab_spectral(h, dptr(recv), 1, stream))
+            spec.append(after(main))
+            with torch.cuda.stream(comm):
+                comm.wait_event(spec[c])
+                dist.all_to_all_single(send, recv)
+                a2a2.append(after(comm))
+        for c in range(ncomp):
+            send, _ = self._slab_bufs[c]
+            main.wait_event(a2a2[c])
+            _lib.check(lib, lib.sb200_poisson_slab_backward(h, comp_ptr(sp, c), 1, dptr(send), stream))
 
     def solve(self, solution_field, rhs_field):
         """-del^2(solution_field) = rhs_field on the unbounded domain; padded local
