@@ -39,8 +39,29 @@ WORKLOADS = {
     "vortex_ring_128_f32": ((128, 128, 128), "navier_stokes", False),
     "vortex_ring_512_f32": ((512, 512, 512), "navier_stokes", False),
     "sphere_vbf_512x256x256_f32": ((256, 256, 512), "navier_stokes_with_forcing", True),
+    # BASELINE configs[3]: rod in cross-flow; x_range 1.8, Laplacian filter order 1 (multiplicative),
+    # synthetic rod surface grid (160 rings x 64 points + caps ~ 10 k points), 3 velocity
+    # interpolations (rod sub-steps) + 1 full interaction per flow step
+    "rod_fsi_512x256x256_f32": ((256, 256, 512), "navier_stokes_with_forcing", "rod"),
     "fsi_512_f32": ((512, 512, 512), "navier_stokes_with_forcing", True),
 }
+
+
+def rod_surface_points(x_range, y_range, z_range, n_elem=160, n_ring=64):
+    """Straight rod of length 1 along x, diameter y_range / 5, centred in the box."""
+    length, radius = 1.0, y_range / 10.0
+    x0 = 0.5 * (x_range - length)
+    xs = x0 + (np.arange(n_elem) + 0.5) * length / n_elem
+    th = 2 * np.pi * np.arange(n_ring) / n_ring
+    ring = np.stack([np.zeros(n_ring), radius * np.cos(th), radius * np.sin(th)])
+    pts = [np.stack([np.full(n_ring, x), 0.5 * y_range + ring[1], 0.5 * z_range + ring[2]]) for x in xs]
+    for xc in (x0, x0 + length):  # caps: concentric rings
+        for frac in (0.25, 0.5, 0.75):
+            m = max(int(n_ring * frac), 4)
+            t2 = 2 * np.pi * np.arange(m) / m
+            pts.append(np.stack([np.full(m, xc), 0.5 * y_range + frac * radius * np.cos(t2),
+                                 0.5 * z_range + frac * radius * np.sin(t2)]))
+    return np.concatenate(pts, axis=1)
 
 
 def vortex_ring(x, y, z, real_t):
@@ -215,10 +236,13 @@ def main():
             axis += 1
     real_t = np.float32
     nu = 1.0 / 1000.0  # Re_Gamma = 1000
+    is_rod = with_body == "rod"
+    with_body = bool(with_body)
+    extra = dict(filter_vorticity=True, filter_setting_dict={"order": 1, "type": "multiplicative"}) if is_rod else {}
     sim = UnboundedFlowSimulator3D(
-        grid_size=tuple(grid), x_range=1.0, kinematic_viscosity=nu, flow_type=flow_type, real_t=real_t,
-        with_free_stream_flow=with_body, use_fused_kernels=not args.no_fused,
-        poisson_backend=args.poisson_backend, rank_distribution=(0, 1, 1))
+        grid_size=tuple(grid), x_range=1.8 if is_rod else 1.0, kinematic_viscosity=nu, flow_type=flow_type,
+        real_t=real_t, with_free_stream_flow=with_body, use_fused_kernels=not args.no_fused,
+        poisson_backend=args.poisson_backend, rank_distribution=(0, 1, 1), **extra)
     gs = sim.ghost_size
     x = sim.local_x[None, None, :].astype(np.float64)
     y = sim.local_y[None, :, None].astype(np.float64)
@@ -237,7 +261,12 @@ def main():
     if with_body:
         dx = float(sim.dx)
         diameter = 0.4 * min(grid[0], grid[1]) / grid[2]
-        pts = sphere_points((0.25, 0.5 * sim.y_range, 0.5 * sim.z_range), diameter, dx)
+        if is_rod:
+            pts = rod_surface_points(sim.x_range, sim.y_range, sim.z_range)
+            lag_vel = 0.01 * np.random.default_rng(1234).standard_normal(pts.shape)
+        else:
+            pts = sphere_points((0.25, 0.5 * sim.y_range, 0.5 * sim.z_range), diameter, dx)
+            lag_vel = None
         n_lag = pts.shape[1]
 
         class _Body:
@@ -257,6 +286,9 @@ def main():
     def one_step():
         dt = sim.compute_stable_timestep(dt_prefac=0.5)
         if interactor is not None:
+            if is_rod:  # rod sub-steps: flow forces on the body only (velocity interpolation + force)
+                for _ in range(3):
+                    interactor.compute_flow_forces_and_torques()
             interactor()
             interactor.time_step(dt)
         sim.time_step(dt=dt, free_stream_velocity=u_inf)

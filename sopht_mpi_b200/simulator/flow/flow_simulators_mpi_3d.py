@@ -405,17 +405,26 @@ class UnboundedFlowSimulator3D:
         """reference :426-449; max over interior of sum |u_i| comes from the fused velocity
         sweep when the velocity has not been touched from the host since."""
         tol = get_test_tol(precision)
-        if (self._max_abs_vel_version is not None
+        if not (self._max_abs_vel_version is not None
                 and self._max_abs_vel_version == self.velocity_field.version):
-            max_vel = float(self._max_abs_vel_dev.item())
-        else:
-            max_vel = self._reduce("sb200_max_abs_sum", self.velocity_field, self.grid_dim)
-        max_vel = self.real_t(max_vel)
+            ctx = self._ctx
+            ctx.call("sb200_max_abs_sum", ctx.gref, dptr(self.velocity_field.tensor), self.grid_dim,
+                     dptr(self._max_abs_vel_dev), ctx.stream())
+            self._max_abs_vel_version = self.velocity_field.version
+        max_dev = self._max_abs_vel_dev
+        if self._ctx.distributed:
+            # dt = min over ranks of a decreasing function of the local maximum = that function of the
+            # global maximum: one NCCL all-reduce of the device scalar replaces the reference's host
+            # allreduce(MIN) (flow_simulators_mpi_3d.py:447-448) and its host round trip per rank
+            import torch.distributed as dist
+
+            max_dev = self._max_abs_vel_dev.clone()
+            dist.all_reduce(max_dev, op=dist.ReduceOp.MAX)
+        max_vel = self.real_t(float(max_dev.item()))
         dt = min(
             self.CFL * self.dx / (max_vel + tol),
             0.9 * self.dx ** 2 / (2 * self.grid_dim) / (self.kinematic_viscosity + tol),
         )
-        dt = self.mpi_construct.grid.allreduce(dt, op=MPI.MIN)
         return dt * dt_prefac
 
     def get_vorticity_divergence_l2_norm(self):
