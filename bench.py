@@ -353,7 +353,9 @@ def main():
         solver.set_profiling(False)
         stage_ms.update({"poisson_" + k: v for k, v in acc.items()})
         zk = "z_fused_forward_green_inverse"
-        z_bytes = 8 * w_bytes * 3 * local_cells
+        if zk not in acc:  # z-slabs: the y and z passes are timed together (20 W per cell and component)
+            zk = "y_forward_z_fused_y_inverse"
+        z_bytes = (8 if zk.startswith("z_") else 20) * w_bytes * 3 * local_cells
         achieved = z_bytes / (acc[zk] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "sb_fft_strided_kernel<float, MODE 1> (fused z pass of the Poisson "
                     "vector solve: forward FFT x Green x inverse FFT, in place)",
@@ -361,19 +363,20 @@ def main():
                     "traffic": NCU_Z_PASS_TRAFFIC_BYTES.get(name) if world == 1 else None,
                     "peak_source": peak_src,
                     "launch_ms": acc[zk], "algorithmic_bytes_per_launch": z_bytes,
-                    "algorithmic_bytes_per_cell": 8 * w_bytes * 3,
+                    "algorithmic_bytes_per_cell": z_bytes / local_cells,
                     "share_of_step": acc[zk] / stage_ms["full_step"],
                     "per_gpu": world > 1,
                     "note": "the kernel is co-limited by FP32 issue (radix-16 butterflies, ~33 lane-ops per "
                             "complex point and transform) and HBM; see profiles/r01_fft_tuning.md"}
     nvlink = None
-    if world > 1 and "poisson_all_to_all_z_to_ky" in stage_ms:
-        # each all-to-all moves the y-pass output (2 W per cell-of-the-doubled-y-axis ... complex, 2ny x (nx+2))
-        # of this GPU's planes, minus the block that stays local
-        a2a_bytes = 2 * w_bytes * 3 * (grid[0] / world) * 2 * grid[1] * (grid[2] + 2) * (world - 1) / world
+    if world > 1 and "poisson_all_to_all_z_to_kx" in stage_ms:
+        # each all-to-all moves the x-pass output (nx/2 + 1 complex bins per row = 2 W per cell) of this
+        # GPU's planes, minus the block that stays local
+        kxl = ((grid[2] + 1 + world - 1) // world + 3) // 4 * 4
+        a2a_bytes = 2 * w_bytes * 3 * (grid[0] / world) * grid[1] * kxl * (world - 1)
         nvlink = {"all_to_all_bytes_out_per_gpu": a2a_bytes,
                   "GBps_out_per_gpu": [a2a_bytes / (stage_ms[k] * 1e-3) / 1e9
-                                       for k in ("poisson_all_to_all_z_to_ky", "poisson_all_to_all_ky_to_z")],
+                                       for k in ("poisson_all_to_all_z_to_kx", "poisson_all_to_all_kx_to_z")],
                   "peak_GBps_per_direction": 900.0}
     poisson_bytes = 86 * w_bytes * local_cells
     poisson_gbs = poisson_bytes / (stage_ms["poisson_vector_solve"] * 1e-3) / 1e9

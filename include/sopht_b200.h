@@ -136,12 +136,16 @@ int64_t sb200_poisson_workspace_bytes(const sb200_poisson_t* p);
 /* z-slab decomposition (nranks = 2, 4 or 8; backend 1): mpi4py-fft's distributed transform
  * (poisson_solver_3d/fft_mpi_3d.py:27-48) and MPIDomainDoublingCommunicator3D
  * (UnboundedPoissonSolverMPI3D.py:190-382) become
- *   slab_forward (local x,y passes -> send_buf, blocked by destination rank)
+ *   slab_forward  (x r2c of the local planes -> send_buf, blocked by destination rank: each rank
+ *                  receives ceil((nx+1)/nranks) kx bins, rounded up to a multiple of 4, of every plane)
  *   all-to-all  send_buf -> recv_buf                       (caller: NCCL)
- *   slab_spectral (fused z forward x Green x z inverse on recv_buf, in place)
+ *   slab_spectral (y forward, fused z forward x Green x z inverse, y inverse; result back in recv_buf)
  *   all-to-all  recv_buf -> send_buf
- *   slab_backward (local y,x inverse passes -> solution interior)
- * Both buffers hold sb200_poisson_slab_buffer_bytes(p, ncomp) bytes. */
+ *   slab_backward (x c2r of the local planes -> solution interior)
+ * The transposes act on the x-pass output, the smallest array of the pipeline (2 reals per cell
+ * instead of 4 after the y pass).  Both buffers hold sb200_poisson_slab_buffer_bytes(p, ncomp)
+ * bytes and must be ZERO-INITIALISED once by the caller (the padding bins of the last kx block are
+ * never written). */
 int64_t sb200_poisson_slab_buffer_bytes(const sb200_poisson_t* p, int ncomp);
 int sb200_poisson_slab_forward(sb200_poisson_t* p, const void* rhs, int ncomp, void* send_buf, void* stream);
 int sb200_poisson_slab_spectral(sb200_poisson_t* p, void* recv_buf, int ncomp, void* stream);

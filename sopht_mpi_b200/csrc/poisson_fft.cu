@@ -76,6 +76,35 @@ struct GreensRows {
   SB_D C2<T> load(int, int z, int y, int m) const { return C2<T>{g(z, y, 2 * m), g(z, y, 2 * m + 1)}; }
 };
 
+// Rows of kx bins either contiguous (pitch elements per row) or, for the x-slab transpose of the
+// distributed solve, split into blocks of kxl bins: bin k of row `line` lives at
+//   (k / kxl) * blk + line * kxl + k % kxl        (one block per destination / source rank)
+// kx bins per rank of the x-slab decomposition: ceil((nx + 1) / nranks) rounded up to a multiple of
+// 4 so that every row of a block starts on a 32-byte sector
+static inline int sb_slab_kxl(int nx, int nranks) { return ((nx + 1 + nranks - 1) / nranks + 3) & ~3; }
+
+struct SbRowBlocks {
+  int kxl = 0;         // 0: contiguous rows
+  unsigned magic = 0;  // ceil(2^32 / kxl): k / kxl == umulhi(k, magic) for k * kxl < 2^32
+  long long blk = 0;
+  SB_D long long at(long long line, long long pitch, int k) const {
+    if (kxl == 0) return line * pitch + k;
+#ifdef SB200_EMU
+    const int b = k / kxl;
+#else
+    const int b = (int)__umulhi((unsigned)k, magic);
+#endif
+    return (long long)b * blk + line * kxl + (k - b * kxl);
+  }
+};
+static inline SbRowBlocks sb_row_blocks(int kxl, long long blk) {
+  SbRowBlocks rb;
+  rb.kxl = kxl;
+  rb.magic = kxl ? (unsigned)((0x100000000ULL + (unsigned long long)kxl - 1) / (unsigned long long)kxl) : 0;
+  rb.blk = blk;
+  return rb;
+}
+
 // ------------------------------------------------------------------ x pass: r2c
 // Real rows of length 2N (second half zero when PRUNED) -> N+1 bins through ONE complex FFT
 // of length N on z[m] = x[2m] + i x[2m+1]:
@@ -83,7 +112,7 @@ struct GreensRows {
 template <typename T, typename Rows, bool PRUNED, int LOG2N, int LINES>
 __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 512)
     sb_fft_x_r2c_kernel(SbFftPlan plan, int lines_rt, Rows rows, C2<T>* out, long long out_pitch,
-                        const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost) {
+                        const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost, SbRowBlocks rb) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
   const int Tn = LOG2N > 0 ? (1 << LOG2N) / SB_FFT_R : plan.threads, N = LOG2N > 0 ? (1 << LOG2N) : plan.n;
@@ -107,7 +136,6 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
   __syncthreads();
   if (valid) {
     const long long line = ((long long)c * gridDim.y + z) * rows.ny + y;
-    C2<T>* row = out + line * out_pitch;
 #pragma unroll
     for (int p = 0; p < SB_FFT_R; ++p) {
       const int k = t + p * Tn;
@@ -115,9 +143,9 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
       const C2<T> zc = cconj(sl.at((N - k) & (N - 1)));
       const C2<T> wd = cmul(wpost[k], csub(zk, zc));
       const C2<T> s = cadd(zk, zc);
-      row[k] = C2<T>{T(0.5) * (s.x + wd.y), T(0.5) * (s.y - wd.x)};
+      out[rb.at(line, out_pitch, k)] = C2<T>{T(0.5) * (s.x + wd.y), T(0.5) * (s.y - wd.x)};
     }
-    if (t == 0) row[N] = C2<T>{v[0].x - v[0].y, T(0)};
+    if (t == 0) out[rb.at(line, out_pitch, N)] = C2<T>{v[0].x - v[0].y, T(0)};
   }
 }
 
@@ -128,7 +156,8 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
 template <typename T, int LOG2N, int LINES>
 __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 512)
     sb_fft_x_c2r_kernel(SbFftPlan plan, int lines_rt, const C2<T>* in, long long in_pitch,
-                        FieldRows<T> rows, const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost) {
+                        FieldRows<T> rows, const C2<T>* __restrict__ tw, const C2<T>* __restrict__ wpost,
+                        SbRowBlocks rb) {
   SB_DYN_SMEM(smem_raw);
   C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
   const int Tn = LOG2N > 0 ? (1 << LOG2N) / SB_FFT_R : plan.threads, N = LOG2N > 0 ? (1 << LOG2N) : plan.n;
@@ -139,11 +168,11 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
   const bool valid = y < rows.ny;
   const int yc = valid ? y : rows.ny - 1;
   const SbSmemLine<T, false> sl = sb_smem_line<T, false>(sm, l, 0, sb_fft_npad(N));
-  const C2<T>* row = in + (((long long)c * gridDim.y + z) * rows.ny + yc) * in_pitch;
+  const long long line = ((long long)c * gridDim.y + z) * rows.ny + yc;
   C2<T> v[SB_FFT_R];
 #pragma unroll
-  for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = row[t + p * Tn];
-  if (t == 0) sl.at(N) = row[N];
+  for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = in[rb.at(line, in_pitch, t + p * Tn)];
+  if (t == 0) sl.at(N) = in[rb.at(line, in_pitch, N)];
   __syncthreads();
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) {
@@ -199,9 +228,12 @@ struct SbGreensTable {
   long long g_pt, g_s1;
   int n1_full = 1;  // full length of the o1 (ky) axis of the table
   int o1_off = 0;   // global ky of this batch's o1 = 0 (slab decomposition)
-  // thread-order copy for the specialised fused z kernel (see sb_greens_thread_order_kernel):
+  // thread-order copy for the specialised fused z kernel (see GreensThreadOrderOp):
   // [m1][kx group][t][line][16 bins of thread t], so a thread's 16 factors are 64 contiguous bytes
   const T* g2 = nullptr;
+  // x-slab decomposition: line i of the batch is global kx = kx0 + i (clamped to the last column
+  // of the table for the zero-filled padding lines)
+  int kx0 = 0, kx_last = 1 << 30;
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS.128); the issuing thread reads its own slot
@@ -302,7 +334,8 @@ __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb
     // k itself (k < n/2), for p >= 8 it is (n - t) - p Tn -> two running pointers, no selects
     const int g1 = o1 + gt.o1_off;
     const int m1 = g1 <= (gt.n1_full >> 1) ? g1 : gt.n1_full - g1;
-    const T* g = gt.g + ((long long)m1 * gt.g_s1 + ic);
+    const int kxg = ic + gt.kx0 < gt.kx_last ? ic + gt.kx0 : gt.kx_last;
+    const T* g = gt.g + ((long long)m1 * gt.g_s1 + kxg);
     const long long gs = (long long)Tn * gt.g_pt;
     const T* ga = g + (long long)t * gt.g_pt;
     const T* gb = g + (long long)(n - t - (SB_FFT_R / 2) * Tn) * gt.g_pt;
@@ -359,6 +392,7 @@ struct GreensThreadOrderOp {
   const T* g;
   long long g_pt, g_s1;
   int n, Tn, lines, nib, pitch;
+  int kx0, inner;  // first global kx of this rank's lines, number of lines
   SB_D void operator()(long long idx) const {
     const int p = (int)(idx & 15);
     long long r = idx >> 4;
@@ -368,8 +402,8 @@ struct GreensThreadOrderOp {
     r /= Tn;
     const int ib = (int)(r % nib);
     const long long m1 = r / nib;
-    const int k = t + p * Tn, mk = k <= (n >> 1) ? k : n - k, kx = ib * lines + l;
-    g2[idx] = kx < pitch ? g[mk * g_pt + m1 * g_s1 + kx] : T(0);
+    const int k = t + p * Tn, mk = k <= (n >> 1) ? k : n - k, i = ib * lines + l, kx = kx0 + i;
+    g2[idx] = (i < inner && kx < pitch) ? g[mk * g_pt + m1 * g_s1 + kx] : T(0);
   }
 };
 
@@ -385,6 +419,7 @@ struct SbFftState {
   long long P = 0;
   size_t bytes = 0;
   int kb = 0;  // ky block size of the B layout (power of two, multiple of 2ny/16, divides 2ny)
+  int kxl = 0; // x-slab decomposition: kx bins per rank (ceil((nx + 1) / nranks))
   // optional per-launch timing (sb200_poisson_set_profiling): events around the five launches
   bool profile = false, have_times = false;
 #ifndef SB200_EMU
@@ -432,56 +467,60 @@ constexpr int sb_xpass_lines(int log2n) { return log2n <= 7 ? 16 : log2n == 8 ? 
 
 template <typename T, typename Rows, bool PRUNED, int LOG2N>
 static int launch_x_r2c_c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
-                          long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+                          long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream,
+                          const SbRowBlocks& rb) {
   constexpr int LINES = LOG2N > 0 ? sb_xpass_lines(LOG2N) : 0;
   const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), false);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
   SB_KERNEL_ATTR_SMEM((sb_fft_x_r2c_kernel<T, Rows, PRUNED, LOG2N, LINES>), smem);
   const dim3 grid((unsigned)((ny + lb - 1) / lb), (unsigned)nz, (unsigned)ncomp);
   SB_LAUNCH_COOP((sb_fft_x_r2c_kernel<T, Rows, PRUNED, LOG2N, LINES>), grid, dim3(lb * plan.threads), smem,
-                 stream, plan, lb, rows, out, pitch, tw, wpost);
+                 stream, plan, lb, rows, out, pitch, tw, wpost, rb);
   SB_CHECK_LAUNCH("fft_x_r2c");
   return 0;
 }
 template <typename T, typename Rows, bool PRUNED>
 static int launch_x_r2c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
-                        long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+                        long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream,
+                        const SbRowBlocks& rb = SbRowBlocks()) {
   if (sizeof(T) == 4 && PRUNED) {
     switch (plan.log2n) {
-      case 8: return launch_x_r2c_c<T, Rows, PRUNED, 8>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
-      case 9: return launch_x_r2c_c<T, Rows, PRUNED, 9>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
-      case 10: return launch_x_r2c_c<T, Rows, PRUNED, 10>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
+      case 8: return launch_x_r2c_c<T, Rows, PRUNED, 8>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream, rb);
+      case 9: return launch_x_r2c_c<T, Rows, PRUNED, 9>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream, rb);
+      case 10: return launch_x_r2c_c<T, Rows, PRUNED, 10>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream, rb);
       default: break;
     }
   }
-  return launch_x_r2c_c<T, Rows, PRUNED, 0>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream);
+  return launch_x_r2c_c<T, Rows, PRUNED, 0>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream, rb);
 }
 
 template <typename T, int LOG2N>
 static int launch_x_c2r_c(const SbFftPlan& plan, int ny, int nz, int ncomp, const C2<T>* in, long long pitch,
-                          const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+                          const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream,
+                          const SbRowBlocks& rb) {
   constexpr int LINES = LOG2N > 0 ? sb_xpass_lines(LOG2N) : 0;
   const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), false);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
   SB_KERNEL_ATTR_SMEM((sb_fft_x_c2r_kernel<T, LOG2N, LINES>), smem);
   const dim3 grid((unsigned)((ny + lb - 1) / lb), (unsigned)nz, (unsigned)ncomp);
   SB_LAUNCH_COOP((sb_fft_x_c2r_kernel<T, LOG2N, LINES>), grid, dim3(lb * plan.threads), smem, stream, plan, lb,
-                 in, pitch, dst, tw, wpost);
+                 in, pitch, dst, tw, wpost, rb);
   SB_CHECK_LAUNCH("fft_x_c2r");
   return 0;
 }
 template <typename T>
 static int launch_x_c2r(const SbFftPlan& plan, int ny, int nz, int ncomp, const C2<T>* in, long long pitch,
-                        const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream) {
+                        const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream,
+                        const SbRowBlocks& rb = SbRowBlocks()) {
   if (sizeof(T) == 4) {
     switch (plan.log2n) {
-      case 8: return launch_x_c2r_c<T, 8>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
-      case 9: return launch_x_c2r_c<T, 9>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
-      case 10: return launch_x_c2r_c<T, 10>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
+      case 8: return launch_x_c2r_c<T, 8>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
+      case 9: return launch_x_c2r_c<T, 9>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
+      case 10: return launch_x_c2r_c<T, 10>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
       default: break;
     }
   }
-  return launch_x_c2r_c<T, 0>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream);
+  return launch_x_c2r_c<T, 0>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
 }
 
 template <typename T, int MODE, int LOG2N>
@@ -564,13 +603,16 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
                "fft backend: slab decomposition needs 2, 4 or 8 ranks");
     SB_REQUIRE(nz % p->nranks == 0 && nz / p->nranks >= 2 * p->gs, "fft backend: nz must split into slabs");
   }
-  // z-slab decomposition: this rank holds nz / nranks planes; B (the y-pass output) then lives in
-  // the caller's exchange buffers
-  const long long nzz = p->dim == 3 ? nz / p->nranks : 1;
-  const size_t a_bytes = sizeof(C2<T>) * 3 * nzz * ny * P;
-  const size_t b_bytes = (p->dim == 3 && p->nranks == 1) ? sizeof(C2<T>) * 3 * nzz * 2 * ny * P : 0;
+  // distributed: the x-pass output goes straight into the caller's exchange buffer (blocked by
+  // destination rank); after the transpose this rank owns kxl kx bins of ALL planes and runs the
+  // y and z passes on B[c][nz][2ny][kxl]
+  st->kxl = p->nranks > 1 ? sb_slab_kxl(nx, p->nranks) : 0;
+  const size_t a_bytes = p->nranks == 1 ? sizeof(C2<T>) * 3 * (size_t)(p->dim == 3 ? nz : 1) * ny * P : 0;
+  const size_t b_bytes = p->dim != 3 ? 0
+                         : p->nranks == 1 ? sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * P
+                                          : sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * st->kxl;
   const size_t g_bytes = sizeof(T) * (p->dim == 3 ? (nz + 1) : 1) * (ny + 1) * P;
-  SB_REQUIRE(SB_DEV_ALLOC(st->A, a_bytes), "fft backend: cannot allocate x-pass buffer");
+  if (a_bytes) SB_REQUIRE(SB_DEV_ALLOC(st->A, a_bytes), "fft backend: cannot allocate x-pass buffer");
   if (b_bytes) SB_REQUIRE(SB_DEV_ALLOC(st->B, b_bytes), "fft backend: cannot allocate y-pass buffer");
   SB_REQUIRE(SB_DEV_ALLOC(st->G, g_bytes), "fft backend: cannot allocate Green's table");
   st->bytes = a_bytes + b_bytes + g_bytes;
@@ -606,12 +648,13 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   if (!e && p->dim == 3 && sizeof(T) == 4 && st->pz.log2n >= 8 && st->pz.log2n <= 11) {
     // thread-order copy for the specialised fused z kernel
     const int lines = sb_strided_lines<T>(st->pz.log2n, 1), Tn = st->pz.threads;
-    const int nib = (nx + 1 + lines - 1) / lines;
+    const int inner = p->nranks > 1 ? st->kxl : nx + 1, kx0 = p->nranks > 1 ? p->rank * st->kxl : 0;
+    const int nib = (inner + lines - 1) / lines;
     const long long count = (long long)(ny + 1) * nib * Tn * lines * SB_FFT_R;
     SB_REQUIRE(SB_DEV_ALLOC(st->G2, sizeof(T) * count), "fft backend: cannot allocate the thread-order table");
     st->bytes += sizeof(T) * count;
     e = sb_launch_flat(count, GreensThreadOrderOp<T>{st->G2, st->G, (long long)(ny + 1) * P, P, 2 * nz, Tn, lines,
-                                                     nib, (int)P},
+                                                     nib, (int)P, kx0, inner},
                        stream, "greens_thread_order");
   }
   SB_STREAM_SYNC(stream);
@@ -738,28 +781,40 @@ int sb_poisson_fft_create(sb200_poisson* p, void* stream) {
 }
 
 // ------------------------------------------------------------------ z-slab entry points
-// rank r of P holds planes [r nz/P, (r+1) nz/P).  forward: x r2c + y forward on the local planes,
-// written as P blocks of ky (one per destination rank): S[kyb][c][zl][ky_in][kx].  After the
-// all-to-all every rank owns all z for its ky block, R[zb][c][zl][ky_in][kx]; spectral runs the
-// fused z pass in place; the second all-to-all returns the blocks; backward = y inverse + x c2r.
+// rank r of P holds planes [r nz/P, (r+1) nz/P).  The transpose happens where the data is smallest
+// (2 W per cell instead of 4 W after the y pass):
+//   forward : x r2c of the local planes, written as P blocks of kxl = ceil((nx+1)/P) kx bins, one
+//             per destination rank:                      S[kxb][c][zl][y][kx_in]
+//   all-to-all -> every rank owns its kx block of ALL planes: R[zb][c][zl][y][kx_in]
+//   spectral: y forward R -> B[c][z][ky][kx_in], fused z pass in place on B (Green's table columns
+//             kx0 + kx_in), y inverse B -> R (same blocked-by-z layout)
+//   all-to-all back, backward: x c2r of the local planes from S.
+// Bins beyond nx (the padding of the last block) are never written: the buffers must be
+// zero-initialised once by the caller.
 template <typename T>
-static void slab_lines(const sb200_poisson* p, const SbFftState<T>* st, int ncomp, SbLines* la, SbLines* lb,
-                       SbLines* lz) {
-  const int P_ = p->nranks, nzl = p->nz / P_, ny = p->ny, nx = p->nx;
-  const long long P = st->P;
-  const int kyl = 2 * ny / P_;
-  const long long blk = (long long)ncomp * nzl * kyl * P;  // one destination / source block
-  *la = SbLines{nx + 1, nzl, ncomp, (long long)ny * P, (long long)nzl * ny * P, P};
-  *lb = SbLines{nx + 1, nzl, ncomp, (long long)kyl * P, (long long)nzl * kyl * P, P};
-  int q = 0;
-  while ((st->py.threads << q) < kyl) ++q;
-  lb->qs = q;
-  lb->bstride = blk;
-  *lz = SbLines{nx + 1, kyl, ncomp, P, (long long)nzl * kyl * P, (long long)kyl * P};
-  int qz = 0;
-  while ((st->pz.threads << qz) < nzl) ++qz;
-  lz->qs = qz;
-  lz->bstride = blk;
+struct SbSlabPlan {
+  int nzl, kxl, zl_shift;
+  long long blk;       // elements of one destination / source block
+  SbLines lr, lbuf, lz;  // R lines along y, B lines along y, B lines along z
+};
+template <typename T>
+static SbSlabPlan<T> slab_plan(const sb200_poisson* p, const SbFftState<T>* st, int ncomp) {
+  SbSlabPlan<T> s;
+  const int P_ = p->nranks, nz = p->nz, ny = p->ny;
+  s.nzl = nz / P_;
+  s.kxl = st->kxl;
+  s.zl_shift = 0;
+  while ((1 << s.zl_shift) < s.nzl) ++s.zl_shift;
+  const long long kxl = s.kxl;
+  s.blk = (long long)ncomp * s.nzl * ny * kxl;
+  // R[zb][c][zl][y][kx]: lines (kx, z, c), points along y
+  s.lr = SbLines{s.kxl, nz, ncomp, (long long)ny * kxl, (long long)s.nzl * ny * kxl, kxl};
+  s.lr.o1_shift = s.zl_shift;
+  s.lr.s1_hi = s.blk;
+  // B[c][z][ky][kx]: lines (kx, z, c) along ky, and lines (kx, ky, c) along z
+  s.lbuf = SbLines{s.kxl, nz, ncomp, 2LL * ny * kxl, (long long)nz * 2 * ny * kxl, kxl};
+  s.lz = SbLines{s.kxl, 2 * ny, ncomp, kxl, (long long)nz * 2 * ny * kxl, 2LL * ny * kxl};
+  return s;
 }
 
 template <typename T>
@@ -767,39 +822,34 @@ static int slab_forward_t(sb200_poisson* p, const void* rhs, int ncomp, void* se
   auto* st = (SbFftState<T>*)p->backend_state;
   const int nzl = p->nz / p->nranks, ny = p->ny, nx = p->nx, gs = p->gs;
   const long long my = ny + 2 * gs, mx = nx + 2 * gs, vol = (nzl + 2LL * gs) * my * mx;
-  SbLines la, lb, lz;
-  slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
-  int e;
+  const SbSlabPlan<T> sp = slab_plan<T>(p, st, ncomp);
   FieldRows<T> src{(T*)rhs, ny, gs, 3, my, mx, vol};
-  if ((e = launch_x_r2c<T, FieldRows<T>, true>(st->px, ny, nzl, ncomp, src, st->A, st->P, st->twx, st->wpost,
-                                               stream)))
-    return e;
-  SbGreensTable<T> none{nullptr, 0, 0};
-  return launch_strided<T, 0>(st->py, st->A, la, (C2<T>*)send, lb, st->twy, none, stream);
+  return launch_x_r2c<T, FieldRows<T>, true>(st->px, ny, nzl, ncomp, src, (C2<T>*)send, 0, st->twx, st->wpost,
+                                             stream, sb_row_blocks(sp.kxl, sp.blk));
 }
 template <typename T>
 static int slab_spectral_t(sb200_poisson* p, void* recv, int ncomp, void* stream) {
   auto* st = (SbFftState<T>*)p->backend_state;
-  SbLines la, lb, lz;
-  slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
-  const int kyl = 2 * p->ny / p->nranks;
-  SbGreensTable<T> gt{st->G, (long long)(p->ny + 1) * st->P, st->P, 2 * p->ny, p->rank * kyl};
+  const SbSlabPlan<T> sp = slab_plan<T>(p, st, ncomp);
+  SbGreensTable<T> none{nullptr, 0, 0};
+  int e;
+  if ((e = launch_strided<T, 0>(st->py, (const C2<T>*)recv, sp.lr, st->B, sp.lbuf, st->twy, none, stream))) return e;
+  SbGreensTable<T> gt{st->G, (long long)(p->ny + 1) * st->P, st->P, 2 * p->ny, 0};
   gt.g2 = st->G2;
-  return launch_strided<T, 1>(st->pz, (const C2<T>*)recv, lz, (C2<T>*)recv, lz, st->twz, gt, stream);
+  gt.kx0 = p->rank * sp.kxl;
+  gt.kx_last = (int)st->P - 1;
+  if ((e = launch_strided<T, 1>(st->pz, st->B, sp.lz, st->B, sp.lz, st->twz, gt, stream))) return e;
+  return launch_strided<T, 2>(st->py, st->B, sp.lbuf, (C2<T>*)recv, sp.lr, st->twy, none, stream);
 }
 template <typename T>
 static int slab_backward_t(sb200_poisson* p, void* solution, int ncomp, const void* send, void* stream) {
   auto* st = (SbFftState<T>*)p->backend_state;
   const int nzl = p->nz / p->nranks, ny = p->ny, nx = p->nx, gs = p->gs;
   const long long my = ny + 2 * gs, mx = nx + 2 * gs, vol = (nzl + 2LL * gs) * my * mx;
-  SbLines la, lb, lz;
-  slab_lines<T>(p, st, ncomp, &la, &lb, &lz);
-  SbGreensTable<T> none{nullptr, 0, 0};
-  int e = launch_strided<T, 2>(st->py, (const C2<T>*)send, lb, st->A, la, st->twy, none, stream);
-  if (e) return e;
+  const SbSlabPlan<T> sp = slab_plan<T>(p, st, ncomp);
   FieldRows<T> dst{(T*)solution, ny, gs, 3, my, mx, vol};
-  return launch_x_c2r<T>(st->px, ny, nzl, ncomp, (const C2<T>*)st->A, st->P, dst, (const C2<T>*)st->twx,
-                         (const C2<T>*)st->wpost, stream);
+  return launch_x_c2r<T>(st->px, ny, nzl, ncomp, (const C2<T>*)send, 0, dst, (const C2<T>*)st->twx,
+                         (const C2<T>*)st->wpost, stream, sb_row_blocks(sp.kxl, sp.blk));
 }
 
 static int slab_check(const sb200_poisson* p, int ncomp) {
@@ -811,7 +861,8 @@ static int slab_check(const sb200_poisson* p, int ncomp) {
 extern "C" int64_t sb200_poisson_slab_buffer_bytes(const sb200_poisson_t* p, int ncomp) {
   if (!p || p->nranks < 1) return 0;
   const int64_t w = p->dtype == SB200_F32 ? 4 : 8;
-  return 2 * w * ncomp * (int64_t)(p->nz / p->nranks) * 2 * p->ny * (p->nx + 2);
+  const int64_t kxl = sb_slab_kxl(p->nx, p->nranks);
+  return 2 * w * ncomp * (int64_t)(p->nz / p->nranks) * p->ny * kxl * p->nranks;
 }
 extern "C" int sb200_poisson_slab_forward(sb200_poisson_t* p, const void* rhs, int ncomp, void* send_buf,
                                           void* stream) {

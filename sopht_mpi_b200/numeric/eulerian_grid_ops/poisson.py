@@ -63,8 +63,8 @@ class _UnboundedPoissonSolver:
 
     STAGE_NAMES = ("x_r2c", "y_forward", "z_fused_forward_green_inverse", "y_inverse", "x_c2r")
 
-    SLAB_STAGE_NAMES = ("local_x_r2c_y_forward", "all_to_all_z_to_ky", "z_fused_forward_green_inverse",
-                        "all_to_all_ky_to_z", "local_y_inverse_x_c2r")
+    SLAB_STAGE_NAMES = ("local_x_r2c", "all_to_all_z_to_kx", "y_forward_z_fused_y_inverse",
+                        "all_to_all_kx_to_z", "local_x_c2r")
 
     def set_profiling(self, enable=True):
         """Record CUDA events around the launches of a solve (single rank: the five kernels, inside
@@ -94,9 +94,10 @@ class _UnboundedPoissonSolver:
         st.finish()
 
     def _solve_slabs(self, s, r, ncomp, stream):
-        """z-slab solve: local x/y passes, all-to-all (z <-> ky), fused z pass, all-to-all back,
-        local inverse passes.  The transposes replace mpi4py-fft's and the domain-doubling copies
-        (reference ``UnboundedPoissonSolverMPI3D.py:190-382``, ``fft_mpi_3d.py:27-48``).
+        """z-slab solve: local x pass, all-to-all (z-slabs <-> kx-slabs, on the x-pass output: the
+        smallest array of the pipeline), y / fused z / inverse y passes on the kx-slab, all-to-all
+        back, local inverse x pass.  The transposes replace mpi4py-fft's and the domain-doubling
+        copies (reference ``UnboundedPoissonSolverMPI3D.py:190-382``, ``fft_mpi_3d.py:27-48``).
 
         The components are software-pipelined: each has its own pair of exchange buffers, the
         kernels run on the caller's stream and the NCCL all-to-alls on a second stream, so the
@@ -108,8 +109,9 @@ class _UnboundedPoissonSolver:
         lib, h = self.lib, self._handle
         if not self._slab_bufs:
             nfloat = int(lib.sb200_poisson_slab_buffer_bytes(h, 1)) // 4
-            self._slab_bufs = [(torch.empty(nfloat, dtype=torch.float32, device=self.device),
-                                torch.empty(nfloat, dtype=torch.float32, device=self.device))
+            # zero-initialised: the padding kx bins of the last block are never written
+            self._slab_bufs = [(torch.zeros(nfloat, dtype=torch.float32, device=self.device),
+                                torch.zeros(nfloat, dtype=torch.float32, device=self.device))
                                for _ in range(3)]
             # high priority: the NCCL kernels must get SMs while a transform kernel still has blocks queued
             self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1)

@@ -308,6 +308,70 @@ def test_pruned_fft_poisson_pipeline_3d(real_t, n):
     assert np.all(sol[:, 0] == 7.0) and np.all(sol[:, :, :, -1] == 7.0)  # ghosts untouched
 
 
+def _slab_solve_emulated(lib, real_t, n, nranks, rhs, gs, ncomp):
+    """Run the z-slab entry points of `nranks` handles in this process; the two all-to-alls are
+    numpy block transposes (what NCCL's all_to_all_single does with equal splits)."""
+    nzl = n[0] // nranks
+    handles = []
+    for r in range(nranks):
+        h = ctypes.c_void_p()
+        _lib.check(lib, lib.sb200_poisson_create(ctypes.byref(h), 3, _lib.dtype_code(real_t), n[0], n[1], n[2],
+                                                 gs, 1.0, r, nranks, 1, None))
+        handles.append(h)
+    nbytes = int(lib.sb200_poisson_slab_buffer_bytes(handles[0], ncomp))
+    itemsize = np.dtype(real_t).itemsize
+    send = [np.zeros(nbytes // itemsize, real_t) for _ in range(nranks)]
+    recv = [np.zeros(nbytes // itemsize, real_t) for _ in range(nranks)]
+    local = [np.ascontiguousarray(rhs[:, r * nzl:r * nzl + nzl + 2 * gs]) for r in range(nranks)]
+    out = [np.full_like(a, 7.0) for a in local]
+
+    def all_to_all(dst, src):
+        blk = src[0].size // nranks
+        for r in range(nranks):
+            for q in range(nranks):
+                dst[r][q * blk:(q + 1) * blk] = src[q][r * blk:(r + 1) * blk]
+
+    for r in range(nranks):
+        _lib.check(lib, lib.sb200_poisson_slab_forward(handles[r], ptr(local[r]), ncomp, ptr(send[r]), None))
+    all_to_all(recv, send)
+    for r in range(nranks):
+        _lib.check(lib, lib.sb200_poisson_slab_spectral(handles[r], ptr(recv[r]), ncomp, None))
+    all_to_all(send, recv)
+    for r in range(nranks):
+        _lib.check(lib, lib.sb200_poisson_slab_backward(handles[r], ptr(out[r]), ncomp, ptr(send[r]), None))
+        lib.sb200_poisson_destroy(handles[r])
+    return out
+
+
+@pytest.mark.parametrize("real_t,n,nranks", [
+    (np.float64, (16, 8, 32), 2), (np.float64, (32, 16, 16), 4), (np.float32, (128, 8, 16), 2),
+    (np.float32, (16, 128, 32), 2), (np.float32, (32, 8, 256), 8),
+], ids=lambda v: str(v) if not isinstance(v, type) else v.__name__)
+def test_slab_decomposed_poisson_pipeline(real_t, n, nranks):
+    """The distributed (z-slab) solve, all ranks emulated in one process, against the scipy oracle."""
+    from emu_util import emu
+    from oracle.poisson import UnboundedPoissonSolverOracle3D
+
+    lib = emu()
+    gs, ncomp = 2, 2
+    rng = np.random.default_rng(1)
+    shape = tuple(v + 2 * gs for v in n)
+    rhs = rng.uniform(size=(ncomp,) + shape).astype(real_t)
+    out = _slab_solve_emulated(lib, real_t, n, nranks, rhs, gs, ncomp)
+    oracle = UnboundedPoissonSolverOracle3D(*n, x_range=1.0, real_t=real_t)
+    ref = np.zeros_like(rhs)
+    for c in range(ncomp):
+        oracle.solve(ref[c], rhs[c], gs)
+    nzl = n[0] // nranks
+    tol = 1e-13 if real_t == np.float64 else 2e-6
+    scale = np.abs(ref).max()
+    for r in range(nranks):
+        got = out[r][:, gs:-gs, gs:-gs, gs:-gs]
+        want = ref[:, r * nzl + gs:r * nzl + gs + nzl, gs:-gs, gs:-gs]
+        assert np.abs(got - want).max() / scale < tol, (r, np.abs(got - want).max() / scale)
+        assert np.all(out[r][:, 0] == 7.0) and np.all(out[r][:, :, :, -1] == 7.0)  # ghosts untouched
+
+
 @pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
 def test_pruned_fft_poisson_pipeline_2d(real_t):
     from emu_util import emu
