@@ -377,7 +377,8 @@ def main():
         nvlink = {"all_to_all_bytes_out_per_gpu": a2a_bytes,
                   "GBps_out_per_gpu": [a2a_bytes / (stage_ms[k] * 1e-3) / 1e9
                                        for k in ("poisson_all_to_all_z_to_kx", "poisson_all_to_all_kx_to_z")],
-                  "peak_GBps_per_direction": 900.0}
+                  "peak_GBps_per_direction": 900.0,
+                  "exchange": getattr(solver, "exchange_mode", None)}
     poisson_bytes = 86 * w_bytes * local_cells
     poisson_gbs = poisson_bytes / (stage_ms["poisson_vector_solve"] * 1e-3) / 1e9
     step_bytes = (107 if flow_type == "navier_stokes_with_forcing" else 101) * w_bytes * local_cells

@@ -158,6 +158,12 @@ int sb200_poisson_slab_backward(sb200_poisson_t* p, void* solution, int ncomp, c
  * time the dominant kernel live, inside its timed region. */
 int sb200_poisson_set_profiling(sb200_poisson_t* p, int enable);
 int sb200_poisson_last_stage_ms(sb200_poisson_t* p, float* ms_out, int n);
+/* NVLink peer copies for the transposes (replace the MPI Alltoallw inside mpi4py-fft,
+ * poisson_solver_3d/fft_mpi_3d.py:27-48): `dst` is a pointer into another rank's exchange buffer,
+ * mapped into this process through CUDA IPC by the caller.  enable_peer_access is called once per
+ * device pair; peer_copy enqueues a copy-engine transfer on `stream`. */
+int sb200_enable_peer_access(int device, int peer_device);
+int sb200_peer_copy(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

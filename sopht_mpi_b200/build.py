@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libsophtb200.so")
 SOURCES = ["stencils.cu", "reduce.cu", "ib.cu", "poisson.cu", "poisson_cufft.cu", "poisson_fft.cu",
-           "fused.cu"]
+           "fused.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -108,11 +108,16 @@ class _UnboundedPoissonSolver:
 
         lib, h = self.lib, self._handle
         if not self._slab_bufs:
+            import os
+
+            from ...utils.peer import PeerExchange
+
             nfloat = int(lib.sb200_poisson_slab_buffer_bytes(h, 1)) // 4
-            # zero-initialised: the padding kx bins of the last block are never written
-            self._slab_bufs = [(torch.zeros(nfloat, dtype=torch.float32, device=self.device),
-                                torch.zeros(nfloat, dtype=torch.float32, device=self.device))
-                               for _ in range(3)]
+            # per component a (send, recv) pair, visible to the other ranks through CUDA IPC
+            self._peer = PeerExchange(6, nfloat, self.device, self.mpi_construct.rank, self.mpi_construct.size,
+                                      use_peer_copies=os.environ.get("SB200_NO_PEER_COPIES") is None)
+            self.exchange_mode = self._peer.mode
+            self._slab_bufs = [(self._peer.local[2 * c], self._peer.local[2 * c + 1]) for c in range(3)]
             # high priority: the NCCL kernels must get SMs while a transform kernel still has blocks queued
             self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
         main = torch.cuda.current_stream(self.device)
@@ -139,13 +144,13 @@ class _UnboundedPoissonSolver:
                                                                stream))
             mark()
             for c in range(ncomp):
-                dist.all_to_all_single(self._slab_bufs[c][1], self._slab_bufs[c][0])
+                self._peer.exchange(2 * c + 1, 2 * c)
             mark()
             for c in range(ncomp):
                 _lib.check(lib, lib.sb200_poisson_slab_spectral(h, dptr(self._slab_bufs[c][1]), 1, stream))
             mark()
             for c in range(ncomp):
-                dist.all_to_all_single(self._slab_bufs[c][0], self._slab_bufs[c][1])
+                self._peer.exchange(2 * c, 2 * c + 1)
             mark()
             for c in range(ncomp):
                 _lib.check(lib, lib.sb200_poisson_slab_backward(h, comp_ptr(sp, c), 1,
@@ -169,7 +174,7 @@ class _UnboundedPoissonSolver:
             send, recv = self._slab_bufs[c]
             with torch.cuda.stream(comm):
                 comm.wait_event(fwd[c])
-                dist.all_to_all_single(recv, send)
+                self._peer.exchange(2 * c + 1, 2 * c)
                 a2a1.append(after(comm))
         for c in range(ncomp):
             send, recv = self._slab_bufs[c]
@@ -178,7 +183,7 @@ class _UnboundedPoissonSolver:
             spec.append(after(main))
             with torch.cuda.stream(comm):
                 comm.wait_event(spec[c])
-                dist.all_to_all_single(send, recv)
+                self._peer.exchange(2 * c, 2 * c + 1)
                 a2a2.append(after(comm))
         for c in range(ncomp):
             send, _ = self._slab_bufs[c]

@@ -1,0 +1,89 @@
+"""All-to-all of equal blocks over NVLink peer memory (one process per GPU, one node).
+
+Every rank allocates its exchange buffers, publishes them through CUDA IPC and maps the buffers of
+all other ranks; an exchange is then one device-to-device peer copy per destination, written
+straight into the destination rank's buffer by the copy engines (no SMs, unlike NCCL's send/recv
+kernels, which compete with the transform kernels the exchange is overlapped with), followed by a
+tiny NCCL all-reduce that orders "all blocks have landed" on every rank's stream.  Replaces the MPI
+``Alltoallw`` inside mpi4py-fft's transposes (reference ``poisson_solver_3d/fft_mpi_3d.py:27-48``).
+
+If CUDA IPC is not available (different nodes, no peer access) the exchange falls back to NCCL.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+from torch.multiprocessing.reductions import reduce_tensor
+
+from .. import _lib
+from .comm import host_group
+from .logger import logger
+
+
+class PeerExchange:
+    def __init__(self, n_buffers, n_float32, device, rank, nranks, use_peer_copies=True):
+        self.rank, self.nranks, self.device = rank, nranks, device
+        # zero-initialised (the padding bins of the last kx block are never written)
+        self.local = [torch.zeros(n_float32, dtype=torch.float32, device=device) for _ in range(n_buffers)]
+        self.peer = None
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        if use_peer_copies and nranks > 1:
+            try:
+                self._map_peers()
+            except Exception as exc:  # pragma: no cover - depends on the node
+                logger.warning(f"CUDA IPC peer mapping unavailable ({type(exc).__name__}: {exc}); "
+                               "the transposes use NCCL send/recv")
+                self.peer = None
+        ok = torch.tensor([1.0 if self.peer is not None else 0.0], dtype=torch.float64)
+        if nranks > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=host_group())
+        if ok.item() < 0.5:
+            self.peer = None
+
+    def _map_peers(self):
+        handles = [reduce_tensor(t) for t in self.local]
+        gathered = [None] * self.nranks
+        dist.all_gather_object(gathered, handles, group=host_group())
+        self.peer = []
+        for q in range(self.nranks):
+            if q == self.rank:
+                self.peer.append(self.local)
+            else:
+                self.peer.append([fn(*args) for fn, args in gathered[q]])
+        self._keep = gathered  # the rebuilt storages reference the senders' handles
+        self._lib = _lib.load()
+        self._dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._peer_dev = [self.peer[q][0].device.index for q in range(self.nranks)]
+        for q in range(self.nranks):
+            if q != self.rank:
+                # both directions: without the reverse mapping the driver stages the copy through
+                # the host (25 GB/s instead of ~640 GB/s, profiles/r01_peer_copy.txt)
+                _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._dev, self._peer_dev[q]))
+                _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._peer_dev[q], self._dev))
+
+    @property
+    def mode(self):
+        return "cuda-ipc peer copies" if self.peer is not None else "nccl send/recv"
+
+    def exchange(self, dst, src):
+        """Block q of this rank's buffer `src` -> block `rank` of rank q's buffer `dst`, for every q
+        (buffers are addressed by their index in ``self.local``).  Runs on the current stream."""
+        nranks, rank = self.nranks, self.rank
+        s_blocks = self.local[src].chunk(nranks)
+        if self.peer is None:
+            d_blocks = self.local[dst].chunk(nranks)
+            d_blocks[rank].copy_(s_blocks[rank])
+            empty = self.local[dst][:0]
+            dist.all_to_all([empty if q == rank else d_blocks[q] for q in range(nranks)],
+                            [empty if q == rank else s_blocks[q] for q in range(nranks)])
+            return
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for k in range(nranks):
+            q = (rank + k) % nranks  # start with the local block, then walk the ring
+            d = self.peer[q][dst].chunk(nranks)[rank]
+            _lib.check(self._lib, self._lib.sb200_peer_copy(
+                ctypes.c_void_p(d.data_ptr()), self._peer_dev[q], ctypes.c_void_p(s_blocks[q].data_ptr()),
+                self._dev, s_blocks[q].numel() * 4, stream))
+        # all ranks' copies precede their all-reduce in stream order: past this point every block of
+        # `dst` has landed here, and every rank has finished reading the `src` blocks it was sent
+        dist.all_reduce(self._flag)

@@ -12,7 +12,7 @@ ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "sopht_mpi_b200", "csrc")
 LIB = os.path.join(HERE, "libsb200_emu.so")
 SOURCES = ["stencils.cu", "reduce.cu", "ib.cu", "poisson.cu", "poisson_cufft.cu", "poisson_fft.cu",
-           "fused.cu"]
+           "fused.cu", "peer.cu"]
 
 
 def build(force=False):

@@ -1,0 +1,60 @@
+"""Bandwidth of CUDA-IPC peer copies between two ranks (torchrun --nproc-per-node 2)."""
+import ctypes
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+from torch.multiprocessing.reductions import reduce_tensor
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+from sopht_mpi_b200 import _lib  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl")
+    g = dist.new_group(backend="gloo")
+    lib = _lib.load()
+    n = 64 << 20
+    mine = torch.zeros(n // 4, dtype=torch.float32, device="cuda")
+    src = torch.ones(n // 4, dtype=torch.float32, device="cuda")
+    handles = [None, None]
+    dist.all_gather_object(handles, reduce_tensor(mine), group=g)
+    fn, args = handles[1 - rank]
+    peer = fn(*args)
+    print(rank, "peer tensor device", peer.device, "can access", torch.cuda.can_device_access_peer(rank, 1 - rank), flush=True)
+    for a, b in ((rank, 1 - rank), (1 - rank, rank)):
+        print(rank, "enable", a, b, lib.sb200_enable_peer_access(a, b), flush=True)
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def timed(label, f):
+        f()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            f()
+        b.record()
+        torch.cuda.synchronize()
+        print(rank, label, f"{n * 10 / (a.elapsed_time(b) * 1e-3) / 1e9:.1f} GB/s", flush=True)
+        dist.barrier()
+
+    timed("push cudaMemcpyPeerAsync", lambda: lib.sb200_peer_copy(
+        ctypes.c_void_p(peer.data_ptr()), 1 - rank, ctypes.c_void_p(src.data_ptr()), rank, n, sp))
+    timed("pull cudaMemcpyPeerAsync", lambda: lib.sb200_peer_copy(
+        ctypes.c_void_p(src.data_ptr()), rank, ctypes.c_void_p(peer.data_ptr()), 1 - rank, n, sp))
+    timed("torch copy_ push", lambda: peer.copy_(src, non_blocking=True))
+    other = torch.empty_like(src)
+    timed("nccl send/recv", lambda: dist.batch_isend_irecv(
+        [dist.P2POp(dist.isend, src, 1 - rank), dist.P2POp(dist.irecv, other, 1 - rank)])[-1].wait())
+    dist.barrier()
+    del peer
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
