@@ -84,24 +84,25 @@ struct GreensRows {
 static inline int sb_slab_kxl(int nx, int nranks) { return ((nx + 1 + nranks - 1) / nranks + 3) & ~3; }
 
 struct SbRowBlocks {
-  int kxl = 0;         // 0: contiguous rows
-  unsigned magic = 0;  // ceil(2^32 / kxl): k / kxl == umulhi(k, magic) for k * kxl < 2^32
-  long long blk = 0;
-  SB_D long long at(long long line, long long pitch, int k) const {
-    if (kxl == 0) return line * pitch + k;
+  int kxl = 0;          // 0: contiguous rows
+  unsigned magic = 0;   // ceil(2^32 / kxl): k / kxl == umulhi(k, magic) for k * kxl < 2^32
+  long long dblk = 0;   // block stride minus kxl
+  // element offset of bin k relative to the start of its row in block 0
+  SB_D long long rel(int k) const {
 #ifdef SB200_EMU
     const int b = k / kxl;
 #else
     const int b = (int)__umulhi((unsigned)k, magic);
 #endif
-    return (long long)b * blk + line * kxl + (k - b * kxl);
+    return (long long)b * dblk + k;
   }
+  SB_D long long row(long long line, long long pitch) const { return line * (kxl ? (long long)kxl : pitch); }
 };
 static inline SbRowBlocks sb_row_blocks(int kxl, long long blk) {
   SbRowBlocks rb;
   rb.kxl = kxl;
   rb.magic = kxl ? (unsigned)((0x100000000ULL + (unsigned long long)kxl - 1) / (unsigned long long)kxl) : 0;
-  rb.blk = blk;
+  rb.dblk = blk - kxl;
   return rb;
 }
 
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
   __syncthreads();
   if (valid) {
     const long long line = ((long long)c * gridDim.y + z) * rows.ny + y;
+    C2<T>* row = out + rb.row(line, out_pitch);
+    C2<T> r[SB_FFT_R];
 #pragma unroll
     for (int p = 0; p < SB_FFT_R; ++p) {
       const int k = t + p * Tn;
@@ -143,9 +146,18 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
       const C2<T> zc = cconj(sl.at((N - k) & (N - 1)));
       const C2<T> wd = cmul(wpost[k], csub(zk, zc));
       const C2<T> s = cadd(zk, zc);
-      out[rb.at(line, out_pitch, k)] = C2<T>{T(0.5) * (s.x + wd.y), T(0.5) * (s.y - wd.x)};
+      r[p] = C2<T>{T(0.5) * (s.x + wd.y), T(0.5) * (s.y - wd.x)};
     }
-    if (t == 0) out[rb.at(line, out_pitch, N)] = C2<T>{v[0].x - v[0].y, T(0)};
+    const C2<T> last{v[0].x - v[0].y, T(0)};
+    if (rb.kxl == 0) {  // (block-uniform branch hoisted out of the unrolled stores)
+#pragma unroll
+      for (int p = 0; p < SB_FFT_R; ++p) row[t + p * Tn] = r[p];
+      if (t == 0) row[N] = last;
+    } else {
+#pragma unroll
+      for (int p = 0; p < SB_FFT_R; ++p) row[rb.rel(t + p * Tn)] = r[p];
+      if (t == 0) row[rb.rel(N)] = last;
+    }
   }
 }
 
@@ -169,10 +181,19 @@ __global__ void __launch_bounds__(LOG2N > 0 ? LINES * (1 << LOG2N) / SB_FFT_R : 
   const int yc = valid ? y : rows.ny - 1;
   const SbSmemLine<T, false> sl = sb_smem_line<T, false>(sm, l, 0, sb_fft_npad(N));
   const long long line = ((long long)c * gridDim.y + z) * rows.ny + yc;
+  const C2<T>* row = in + rb.row(line, in_pitch);
   C2<T> v[SB_FFT_R];
+  if (rb.kxl == 0) {  // (block-uniform branch hoisted out of the unrolled loads)
 #pragma unroll
-  for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = in[rb.at(line, in_pitch, t + p * Tn)];
-  if (t == 0) sl.at(N) = in[rb.at(line, in_pitch, N)];
+    for (int p = 0; p < SB_FFT_R; ++p) v[p] = row[t + p * Tn];
+    if (t == 0) sl.at(N) = row[N];
+  } else {
+#pragma unroll
+    for (int p = 0; p < SB_FFT_R; ++p) v[p] = row[rb.rel(t + p * Tn)];
+    if (t == 0) sl.at(N) = row[rb.rel(N)];
+  }
+#pragma unroll
+  for (int p = 0; p < SB_FFT_R; ++p) sl.at(t + p * Tn) = v[p];
   __syncthreads();
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) {
