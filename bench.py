@@ -443,6 +443,13 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        # release the CUDA-IPC mappings of the other ranks' exchange buffers before any rank exits
+        import gc
+
+        del solver, sim, interactor
+        gc.collect()
+        torch.cuda.ipc_collect()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -164,6 +164,8 @@ int sb200_poisson_last_stage_ms(sb200_poisson_t* p, float* ms_out, int n);
  * device pair; peer_copy enqueues a copy-engine transfer on `stream`. */
 int sb200_enable_peer_access(int device, int peer_device);
 int sb200_peer_copy(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream);
+int sb200_peer_copy_blocks(int n, void* const* dst, const int* dst_device, const void* const* src,
+                           int src_device, int64_t bytes, void* stream);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

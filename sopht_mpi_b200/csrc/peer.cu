@@ -41,3 +41,14 @@ extern "C" int sb200_peer_copy(void* dst, int dst_device, const void* src, int s
 #endif
   return 0;
 }
+
+// all blocks of one exchange in a single call: block k goes to dst[k] on device dst_device[k]
+extern "C" int sb200_peer_copy_blocks(int n, void* const* dst, const int* dst_device, const void* const* src,
+                                      int src_device, int64_t bytes, void* stream) {
+  SB_REQUIRE(n >= 0 && dst && dst_device && src, "peer_copy_blocks: bad arguments");
+  for (int k = 0; k < n; ++k) {
+    const int e = sb200_peer_copy(dst[k], dst_device[k], src[k], src_device, bytes, stream);
+    if (e) return e;
+  }
+  return 0;
+}

@@ -265,20 +265,12 @@ class MPIGhostCommunicator:
             t[tuple(lo)] = t[tuple(src_lo)].clone()
             t[tuple(hi)] = t[tuple(src_hi)].clone()
 
-    def exchange_scalar_field_init(self, local_field):
-        t, _ = _tensor_of(local_field)
+    def _plane_ops(self, t):
+        """P2P operations of one scalar field: "up" messages go to the next slab, "down" messages
+        to the previous one; the posting order keeps both directions apart even when prev == next."""
         mc = self.mpi_construct
         gs = self.ghost_size
-        if mc.periodic_domain:
-            self._wrap_local_axes(t)
         prev, nxt = int(mc.previous_grid_along[0]), int(mc.next_grid_along[0])
-        if mc.size == 1:
-            if mc.periodic_domain:
-                t[:gs] = t[-2 * gs:-gs].clone()
-                t[-gs:] = t[gs:2 * gs].clone()
-            return
-        # "up" messages go to the next slab, "down" messages to the previous one; the
-        # posting order (and tag) keeps both directions apart even when prev == next
         ops = []
         if nxt != MPI.PROC_NULL:
             ops.append(dist.P2POp(dist.isend, t[-2 * gs:-gs], nxt, tag=0))
@@ -287,8 +279,27 @@ class MPIGhostCommunicator:
             ops.append(dist.P2POp(dist.isend, t[gs:2 * gs], prev, tag=1))
         if nxt != MPI.PROC_NULL:
             ops.append(dist.P2POp(dist.irecv, t[-gs:], nxt, tag=1))
-        if ops:
+        return ops
+
+    def _exchange_init(self, fields):
+        mc = self.mpi_construct
+        gs = self.ghost_size
+        ops = []
+        for t in fields:
+            if mc.periodic_domain:
+                self._wrap_local_axes(t)
+            if mc.size == 1:
+                if mc.periodic_domain:
+                    t[:gs] = t[-2 * gs:-gs].clone()
+                    t[-gs:] = t[gs:2 * gs].clone()
+                continue
+            ops += self._plane_ops(t)
+        if ops:  # one NCCL group for all planes of all components
             self.comm_requests += dist.batch_isend_irecv(ops)
+
+    def exchange_scalar_field_init(self, local_field):
+        t, _ = _tensor_of(local_field)
+        self._exchange_init([t])
 
     # the reference exposes the three flavours separately; with slab planes they coincide
     exchange_scalar_field_faces_init = exchange_scalar_field_init
@@ -296,8 +307,7 @@ class MPIGhostCommunicator:
 
     def exchange_vector_field_init(self, local_vector_field):
         t, _ = _tensor_of(local_vector_field)
-        for c in range(t.shape[0]):
-            self.exchange_scalar_field_init(t[c])
+        self._exchange_init([t[c] for c in range(t.shape[0])])
 
     def exchange_finalise(self):
         for req in self.comm_requests:

@@ -26,6 +26,7 @@ class PeerExchange:
         # zero-initialised (the padding bins of the last kx block are never written)
         self.local = [torch.zeros(n_float32, dtype=torch.float32, device=device) for _ in range(n_buffers)]
         self.peer = None
+        self._plans = {}
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
         if use_peer_copies and nranks > 1:
             try:
@@ -78,12 +79,15 @@ class PeerExchange:
                             [empty if q == rank else s_blocks[q] for q in range(nranks)])
             return
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for k in range(nranks):
-            q = (rank + k) % nranks  # start with the local block, then walk the ring
-            d = self.peer[q][dst].chunk(nranks)[rank]
-            _lib.check(self._lib, self._lib.sb200_peer_copy(
-                ctypes.c_void_p(d.data_ptr()), self._peer_dev[q], ctypes.c_void_p(s_blocks[q].data_ptr()),
-                self._dev, s_blocks[q].numel() * 4, stream))
+        plan = self._plans.get((dst, src))
+        if plan is None:  # pointer tables of this (dst, src) pair, built once
+            order = [(rank + k) % nranks for k in range(nranks)]  # local block first, then the ring
+            dptr = (ctypes.c_void_p * nranks)(*[self.peer[q][dst].chunk(nranks)[rank].data_ptr() for q in order])
+            ddev = (ctypes.c_int * nranks)(*[self._peer_dev[q] for q in order])
+            sptr = (ctypes.c_void_p * nranks)(*[s_blocks[q].data_ptr() for q in order])
+            plan = self._plans[(dst, src)] = (dptr, ddev, sptr, s_blocks[0].numel() * 4)
+        dptr, ddev, sptr, nbytes = plan
+        _lib.check(self._lib, self._lib.sb200_peer_copy_blocks(nranks, dptr, ddev, sptr, self._dev, nbytes, stream))
         # all ranks' copies precede their all-reduce in stream order: past this point every block of
         # `dst` has landed here, and every rank has finished reading the `src` blocks it was sent
         dist.all_reduce(self._flag)
