@@ -410,7 +410,7 @@ class UnboundedFlowSimulator3D:
             ctx = self._ctx
             ctx.call("sb200_max_abs_sum", ctx.gref, dptr(self.velocity_field.tensor), self.grid_dim,
                      dptr(self._max_abs_vel_dev), ctx.stream())
-            self._max_abs_vel_version = self.velocity_field.version
+            # (not cached: only the fused velocity sweep knows that it was the last writer)
         max_dev = self._max_abs_vel_dev
         if self._ctx.distributed:
             # dt = min over ranks of a decreasing function of the local maximum = that function of the
