@@ -87,6 +87,13 @@ int sb200_laplacian_filter(const sb200_grid_t* g, void* field, int ncomp, int fi
  * last one: 0 = x, 1 = y, 2 = z.  Lets the host exchange halos between passes. */
 int sb200_laplacian_filter_axis(const sb200_grid_t* g, void* filter_flux, const void* field_buffer,
                                 int axis, void* stream);
+/* One stage of the filter chain with the wrapper bookkeeping folded in (out of place):
+ *   out = ring ? 0 : written ? 0.25 (-in(+1) - in(-1) + 2 in) : (first ? out : in);  field -= out if field
+ * (reference laplacian_filter_mpi_3d.py:145-385: seven-region filter + ring clear + buffer copy per
+ * stage, `field -= filter_flux` after the last).  The distributed path calls it between halo
+ * exchanges of `in`; sb200_laplacian_filter chains it on one rank. */
+int sb200_laplacian_filter_stage(const sb200_grid_t* g, void* out, const void* in, int axis, void* field,
+                                 int first, void* stream);
 /* zero the physical-boundary ring of width gs+width (laplacian_filter_mpi_3d.py:118-143) */
 int sb200_clear_physical_ring(const sb200_grid_t* g, void* field, int ncomp, int width, void* stream);
 /* stencil_ops_3d/penalise_field_boundary_mpi_3d.py:185-267.  `factors` is a

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "sb200_divergence": (c_int, [_G, _V, _V, c_double, _V]),
     "sb200_laplacian_filter": (c_int, [_G, _V, c_int, c_int, c_int, _V, _V, _V]),
     "sb200_laplacian_filter_axis": (c_int, [_G, _V, _V, c_int, _V]),
+    "sb200_laplacian_filter_stage": (c_int, [_G, _V, _V, c_int, _V, c_int, _V]),
     "sb200_clear_physical_ring": (c_int, [_G, _V, c_int, c_int, _V]),
     "sb200_penalise_field_boundary": (c_int, [_G, _V, c_int, c_int, _V, _V]),
     "sb200_max_abs_sum": (c_int, [_G, _V, c_int, _V, _V]),

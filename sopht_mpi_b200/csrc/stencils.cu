@@ -274,6 +274,33 @@ struct FilterAxisOp {
   }
 };
 
+// One filter stage with the wrapper's bookkeeping folded in: the reference runs
+// {seven-region filter, ring clear, field_buffer[...] = filter_flux} per stage, i.e. after a stage both
+// arrays hold  ring ? 0 : written ? F(in) : (what the flux array held before),  and "before" equals the
+// stage's own input for every stage but the first (where it is the stale flux array).  Writing that
+// value out of place (ping-pong between the two arrays) saves the copy; the last stage also applies
+// field -= flux (reference laplacian_filter_mpi_3d.py:267-385).
+template <typename T>
+struct FilterStageOp {
+  T* out;
+  const T* in;
+  long long st;
+  T* field;    // non-null on the last stage of a chain
+  int first;   // first stage of a chain: `in` is the field, `out` the (stale) flux array
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    const long long i = g.idx(z, y, x);
+    T v;
+    if (g.in_ring(z, y, x))
+      v = 0;
+    else if (g.written(z, y, x, 1))
+      v = T(0.25) * (-in[i + st] - in[i - st] + T(2) * in[i]);
+    else
+      v = first ? out[i] : in[i];
+    out[i] = v;
+    if (field) field[i] -= v;
+  }
+};
+
 template <typename T>
 struct ClearRingOp {
   T* f;
@@ -372,28 +399,50 @@ static int laplacian_filter_scalar(const sb200_grid_t* gr, const SbGeom& g, T* f
   const long long strides[3] = {1, (long long)g.mx, g.plane};
   const int naxes = g.dim;
   if ((e = sb_launch_cells(g, ClearRingOp<T>{flux}, stream, "filter_clear"))) return e;
-  if (type == 0) {
-    if ((e = sb200_elementwise_copy(gr->dtype, buf, field, g.vol, stream))) return e;
-    for (int it = 0; it < order; ++it)
-      for (int a = 0; a < naxes; ++a) {
-        if ((e = sb_launch_cells(g, FilterAxisOp<T>{flux, buf, strides[a]}, stream, "filter_axis")))
-          return e;
-        if ((e = sb200_elementwise_copy(gr->dtype, buf, flux, g.vol, stream))) return e;
-      }
-    return sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream);
+  if (order == 0) {  // no stage runs: field -= (ring-cleared) flux, once (multiplicative) or per axis
+    for (int a = 0; a < (type == 0 ? 1 : naxes); ++a)
+      if ((e = sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream))) return e;
+    return 0;
   }
-  for (int a = 0; a < naxes; ++a) {
-    if ((e = sb200_elementwise_copy(gr->dtype, buf, field, g.vol, stream))) return e;
-    for (int it = 0; it < order; ++it) {
-      if ((e = sb_launch_cells(g, FilterAxisOp<T>{flux, buf, strides[a]}, stream, "filter_axis")))
-        return e;
-      if ((e = sb200_elementwise_copy(gr->dtype, buf, flux, g.vol, stream))) return e;
+  // a chain of stages ping-pongs flux -> buf -> flux ...; stage 0 reads the field itself
+  auto chain = [&](int nstages, auto axis_of) -> int {
+    const T* in = field;
+    T* out = flux;
+    for (int s = 0; s < nstages; ++s) {
+      // the subtraction rides on the last stage unless that stage still reads the field's neighbours
+      const bool fuse_sub = s == nstages - 1 && s > 0;
+      if (int err = sb_launch_cells(g, FilterStageOp<T>{out, in, strides[axis_of(s)], fuse_sub ? field : nullptr,
+                                                         s == 0},
+                                    stream, "filter_stage"))
+        return err;
+      in = out;
+      out = out == flux ? buf : flux;
     }
-    if ((e = sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream))) return e;
-  }
+    if (nstages == 1)
+      if (int err = sb200_elementwise_saxpby(gr->dtype, field, field, 1.0, flux, -1.0, g.vol, stream)) return err;
+    // the reference leaves the last stage's flux in filter_flux_buffer (the stale values of the next
+    // call's first stage): an even number of stages ended in `buf`
+    if (in != flux) return sb200_elementwise_copy(gr->dtype, flux, buf, g.vol, stream);
+    return 0;
+  };
+  if (type == 0) return chain(order * naxes, [&](int s) { return s % naxes; });
+  for (int a = 0; a < naxes; ++a)
+    if ((e = chain(order, [&](int) { return a; }))) return e;
   return 0;
 }
 
+extern "C" int sb200_laplacian_filter_stage(const sb200_grid_t* gr, void* out, const void* in, int axis,
+                                            void* field, int first, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.gs >= 1, "ghost_size < kernel_support");
+  SB_REQUIRE(axis >= 0 && axis < g.dim && out && in && out != in, "filter_stage: bad arguments");
+  const long long strides[3] = {1, (long long)g.mx, g.plane};
+  SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(g,
+                                                      FilterStageOp<T>{(T*)out, (const T*)in, strides[axis],
+                                                                       (T*)field, first},
+                                                      stream, "filter_stage"));
+}
 extern "C" int sb200_laplacian_filter_axis(const sb200_grid_t* gr, void* flux, const void* buf, int axis,
                                            void* stream) {
   SbGeom g;
@@ -442,6 +491,7 @@ struct PenaliseOp {
   const T* fac;  // [2*dim][gs+w], order z_front,z_back,y_front,y_back,x_front,x_back (2D: y.., x..)
   int w;         // gs + width
   int phase;
+  int ncomp;
   // returns true when index i lies in a physical penalty slab of this axis
   SB_D bool axis(int i, int m, int pf, int pb, int tab, int& ci, T& s, bool& moved) const {
     ci = i;
@@ -471,12 +521,15 @@ struct PenaliseOp {
     if (g.dim == 3) inz = axis(z, g.mz, g.phys[0], g.phys[1], 0, cz, sz, moved);
     if (!(inx || iny || inz)) return;
     if ((phase == 0) != moved) return;
-    T v = f[g.idx(cz, cy, cx)];
-    // multiply by the factors of the slabs this cell belongs to, in X,Y,Z order
-    if (inx) v = v * sx;
-    if (iny) v = v * sy;
-    if (inz) v = v * sz;
-    f[g.idx(z, y, x)] = v;
+    const long long src = g.idx(cz, cy, cx), dst = g.idx(z, y, x);
+    for (int c = 0; c < ncomp; ++c) {  // all components in one launch
+      T v = f[c * g.vol + src];
+      // multiply by the factors of the slabs this cell belongs to, in X,Y,Z order
+      if (inx) v = v * sx;
+      if (iny) v = v * sy;
+      if (inz) v = v * sz;
+      f[c * g.vol + dst] = v;
+    }
   }
 };
 
@@ -508,14 +561,12 @@ extern "C" int sb200_penalise_field_boundary(const sb200_grid_t* gr, void* field
   if (g.phys[3]) add(0, g.mz, g.my - w, g.my, xl, xh);
   if (g.dim == 3 && g.phys[0]) add(0, w, yl, yh, xl, xh);
   if (g.dim == 3 && g.phys[1]) add(g.mz - w, g.mz, yl, yh, xl, xh);
-  for (int c = 0; c < ncomp; ++c)
-    for (int phase = 0; phase < 2; ++phase) {
-      int e = 0;
-      SB_DISPATCH_DTYPE(gr->dtype, e = sb_launch_boxes(g, b,
-                                                       PenaliseOp<T>{(T*)field + (size_t)c * g.vol,
-                                                                     (const T*)factors, w, phase},
-                                                       stream, "penalise"));
-      if (e) return e;
-    }
+  for (int phase = 0; phase < 2; ++phase) {
+    int e = 0;
+    SB_DISPATCH_DTYPE(gr->dtype,
+                      e = sb_launch_boxes(g, b, PenaliseOp<T>{(T*)field, (const T*)factors, w, phase, ncomp},
+                                          stream, "penalise"));
+    if (e) return e;
+  }
   return 0;
 }

@@ -464,27 +464,31 @@ def gen_laplacian_filter_mpi_kernel_3d(mpi_construct, ghost_exchange_communicato
         raise NotImplementedError("filter_flux_buffer_boundary_width != 1")
 
     def _scalar_distributed(f, flux, buf):
-        # same sequence as sb200_laplacian_filter with a halo exchange before each pass
+        # the chain of sb200_laplacian_filter, with a halo exchange of each stage's input
         s = ctx.stream
         ctx.call("sb200_clear_physical_ring", ctx.gref, dptr(flux), 1, 1, s())
 
-        def passes(axes):
-            for a in axes:
-                ctx.exchange_scalar(buf)
-                ctx.call("sb200_laplacian_filter_axis", ctx.gref, dptr(flux), dptr(buf), a, s())
-                buf.copy_(flux)
+        def chain(axes):
+            src, dst = f, flux
+            for k, a in enumerate(axes):
+                ctx.exchange_scalar(src)
+                fuse_sub = k == len(axes) - 1 and k > 0
+                ctx.call("sb200_laplacian_filter_stage", ctx.gref, dptr(dst), dptr(src), a,
+                         dptr(f) if fuse_sub else None, int(k == 0), s())
+                src, dst = dst, (buf if dst is flux else flux)
+            if len(axes) == 1:
+                f.sub_(flux)
+            elif src is not flux:  # the last flux belongs in filter_flux_buffer
+                flux.copy_(buf)
 
-        if type_code == 0:
-            buf.copy_(f)
-            for _ in range(filter_order):
-                passes((0, 1, 2))
-            f.sub_(flux)
+        if filter_order == 0:
+            for _ in range(1 if type_code == 0 else 3):
+                f.sub_(flux)
+        elif type_code == 0:
+            chain([a for _ in range(filter_order) for a in (0, 1, 2)])
         else:
             for a in (0, 1, 2):
-                buf.copy_(f)
-                for _ in range(filter_order):
-                    passes((a,))
-                f.sub_(flux)
+                chain([a] * filter_order)
 
     def _run(field, ncomp):
         st = ctx.stage()

@@ -85,16 +85,21 @@ def test_diffusion_advection_divergence(setup3d):
     assert _rel(d1, d0) < _tol(real_t)
 
 
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("phys", [(1,) * 6, (0, 0, 1, 1, 1, 1), (1, 0, 1, 1, 1, 1)], ids=["single", "inner", "first"])
 @pytest.mark.parametrize("ftype,fname", [(0, "multiplicative"), (1, "convolution")])
-def test_laplacian_filter(setup3d, ftype, fname):
-    real_t, rng, n, gs, shape, g = setup3d
+def test_laplacian_filter(setup3d, ftype, fname, phys, order):
+    """The out-of-place stage chain against the reference sequence (filter, ring clear, buffer copy per
+    stage), including the stale flux values that survive in never-written ghost cells of inner slabs."""
+    real_t, rng, n, gs, shape, _ = setup3d
+    g = _lib.make_grid(3, real_t, gs, n, phys)
     w = rng.uniform(size=(3,) + shape).astype(real_t)
     a0, a1 = w.copy(), w.copy()
     fb0 = rng.uniform(size=shape).astype(real_t)
     fb1 = fb0.copy()
     bb0, bb1 = np.zeros(shape, real_t), np.zeros(shape, real_t)
-    st.laplacian_filter_mpi(a0, fb0, bb0, 2, fname, gs)
-    call("sb200_laplacian_filter", ctypes.byref(g), ptr(a1), 3, 2, ftype, ptr(fb1), ptr(bb1), None)
+    st.laplacian_filter_mpi(a0, fb0, bb0, order, fname, gs, phys)
+    call("sb200_laplacian_filter", ctypes.byref(g), ptr(a1), 3, order, ftype, ptr(fb1), ptr(bb1), None)
     assert _rel(a1, a0) < _tol(real_t) and _rel(fb1, fb0) < _tol(real_t)
 
 
