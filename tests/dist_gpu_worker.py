@@ -48,8 +48,11 @@ def main():
 
         # ---------------- full simulator steps on slabs vs single-domain oracle
         n = (32, 16, 32)
+        # (Laplacian filter on: float64 runs order 1 multiplicative, float32 order 2 convolution)
         kw = dict(grid_size=n, x_range=1.0, kinematic_viscosity=1e-2, flow_type="navier_stokes_with_forcing",
-                  real_t=real_t, with_free_stream_flow=True)
+                  real_t=real_t, with_free_stream_flow=True, filter_vorticity=True,
+                  filter_setting_dict=({"order": 1, "type": "multiplicative"} if real_t == np.float64
+                                       else {"order": 2, "type": "convolution"}))
         sim = UnboundedFlowSimulator3D(rank_distribution=(0, 1, 1), **kw)
         ora = FlowSimulatorOracle3D(**kw)
         zz, yy, xx = np.meshgrid(ora.local_z, ora.local_y, ora.local_x, indexing="ij")
