@@ -254,6 +254,49 @@ SB_D void sb_twiddle_apply(C2<T>* a, const C2<T>* __restrict__ tw, int step) {
   }
 }
 
+// Base twiddles (w^1, w^2, w^4, w^8: log2(R) of them) of one butterfly, loaded ahead of use.
+template <int R>
+struct SbTwBase {
+  static constexpr int N = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
+};
+template <typename T, int R>
+SB_D void sb_twiddle_load(C2<T>* pw, const C2<T>* __restrict__ tw, int step) {
+  pw[0] = tw[step];
+  if (R >= 4) pw[1] = tw[2 * step];
+  if (R >= 8) pw[2] = tw[4 * step];
+  if (R >= 16) pw[3] = tw[8 * step];
+}
+template <typename T, int R>
+SB_D void sb_twiddle_apply_base(C2<T>* a, const C2<T>* pw) {
+  const C2<T> w1 = pw[0];
+  a[1] = cmul(a[1], w1);
+  if (R >= 4) {
+    const C2<T> w2 = pw[1];
+    const C2<T> w3 = cmul(w1, w2);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], w3);
+    if (R >= 8) {
+      const C2<T> w4 = pw[2];
+      const C2<T> w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+      a[4] = cmul(a[4], w4);
+      a[5] = cmul(a[5], w5);
+      a[6] = cmul(a[6], w6);
+      a[7] = cmul(a[7], w7);
+      if (R >= 16) {
+        const C2<T> w8 = pw[3];
+        a[8] = cmul(a[8], w8);
+        a[9] = cmul(a[9], cmul(w1, w8));
+        a[10] = cmul(a[10], cmul(w2, w8));
+        a[11] = cmul(a[11], cmul(w3, w8));
+        a[12] = cmul(a[12], cmul(w4, w8));
+        a[13] = cmul(a[13], cmul(w5, w8));
+        a[14] = cmul(a[14], cmul(w6, w8));
+        a[15] = cmul(a[15], cmul(w7, w8));
+      }
+    }
+  }
+}
+
 // One radix-R stage for the butterflies owned by thread t.
 //   v[p] <-> element t + p*T.  Ns = 2^ns_shift = product of the radices already applied
 //   (always a power of 16 here: non-final stages are radix 16).
@@ -355,8 +398,24 @@ struct SbFftLineC {
   static SB_HD size_t smem_bytes() { return sizeof(C2<T>) * (size_t)LINES * P::npad; }
 };
 
+// base twiddles of the (16 / R) butterflies thread t runs in the radix-R stage that follows Ns points:
+// issued BEFORE the exchange barriers in front of that stage, while the 16 data registers are dead
+// (the points sit in shared memory), so the L1 / L2 latency of the table hides behind the exchange
+template <typename T, int LOG2N, int R, int NS_SHIFT>
+SB_D void sb_fft_stage_twiddles_c(C2<T>* pw, int t, const C2<T>* __restrict__ tw) {
+  using P = SbFftC<LOG2N>;
+  constexpr int M = SB_FFT_R / R;
+  constexpr int LOG2R = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
+  constexpr int Ns = 1 << NS_SHIFT;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int k = (t + m * P::Tn) & (Ns - 1);
+    sb_twiddle_load<T, R>(pw + m * SbTwBase<R>::N, tw, k << (LOG2N - NS_SHIFT - LOG2R));
+  }
+}
+
 template <typename T, int LOG2N, bool LINE_FASTEST, int LINES, int R, int NS_SHIFT, bool LAST>
-SB_D void sb_fft_stage_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+SB_D void sb_fft_stage_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* pw, C2<T>* sl) {
   using P = SbFftC<LOG2N>;
   constexpr int MUL = LINE_FASTEST ? LINES : 1;
   constexpr int M = SB_FFT_R / R;
@@ -369,7 +428,7 @@ SB_D void sb_fft_stage_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ 
     for (int q = 0; q < R; ++q) a[q] = v[m + M * q];
     const int j = t + m * P::Tn;
     const int k = j & (Ns - 1);
-    if constexpr (NS_SHIFT > 0) sb_twiddle_apply<T, R>(a, tw, k << (LOG2N - NS_SHIFT - LOG2R));
+    if constexpr (NS_SHIFT > 0) sb_twiddle_apply_base<T, R>(a, pw + m * SbTwBase<R>::N);
     dft_small<T, R>(a);
     if constexpr (LAST) {
 #pragma unroll
@@ -407,11 +466,22 @@ template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>
 SB_D void sb_fft_forward_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
   using P = SbFftC<LOG2N>;
   static_assert(LOG2N >= 4 && LOG2N <= 12, "supported lengths: 16 .. 4096");
+  constexpr int RLAST = 1 << P::rem;  // closing radix (1: none)
+  C2<T> pw[8];                        // base twiddles of the next stage (at most 8 complex)
+  // radix of the stage that follows `done` radix-16 stages
+#define SB_NEXT_TWIDDLES(done)                                                                   \
+  do {                                                                                           \
+    if constexpr (P::nfull > (done))                                                             \
+      sb_fft_stage_twiddles_c<T, LOG2N, 16, 4 * (done)>(pw, t, tw);                              \
+    else if constexpr (P::rem > 0)                                                               \
+      sb_fft_stage_twiddles_c<T, LOG2N, RLAST, 4 * (done)>(pw, t, tw);                           \
+  } while (0)
   // stage 0
   if constexpr (P::nfull >= 1) {
     constexpr bool last = P::nfull == 1 && P::rem == 0;
-    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 0, last>(v, t, tw, sl);
+    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 0, last>(v, t, pw, sl);
     if constexpr (!last) {
+      SB_NEXT_TWIDDLES(1);
       __syncthreads();
       sb_fft_reread_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, sl);
       __syncthreads();
@@ -419,8 +489,9 @@ SB_D void sb_fft_forward_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict_
   }
   if constexpr (P::nfull >= 2) {
     constexpr bool last = P::nfull == 2 && P::rem == 0;
-    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 4, last>(v, t, tw, sl);
+    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 4, last>(v, t, pw, sl);
     if constexpr (!last) {
+      SB_NEXT_TWIDDLES(2);
       __syncthreads();
       sb_fft_reread_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, sl);
       __syncthreads();
@@ -428,16 +499,18 @@ SB_D void sb_fft_forward_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict_
   }
   if constexpr (P::nfull >= 3) {
     constexpr bool last = P::rem == 0;
-    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 8, last>(v, t, tw, sl);
+    sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 16, 8, last>(v, t, pw, sl);
     if constexpr (!last) {
+      SB_NEXT_TWIDDLES(3);
       __syncthreads();
       sb_fft_reread_c<T, LOG2N, LINE_FASTEST, LINES>(v, t, sl);
       __syncthreads();
     }
   }
-  if constexpr (P::rem == 1) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 2, 4 * P::nfull, true>(v, t, tw, sl);
-  if constexpr (P::rem == 2) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 4, 4 * P::nfull, true>(v, t, tw, sl);
-  if constexpr (P::rem == 3) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 8, 4 * P::nfull, true>(v, t, tw, sl);
+#undef SB_NEXT_TWIDDLES
+  if constexpr (P::rem == 1) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 2, 4 * P::nfull, true>(v, t, pw, sl);
+  if constexpr (P::rem == 2) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 4, 4 * P::nfull, true>(v, t, pw, sl);
+  if constexpr (P::rem == 3) sb_fft_stage_c<T, LOG2N, LINE_FASTEST, LINES, 8, 4 * P::nfull, true>(v, t, pw, sl);
 }
 
 template <typename T, int LOG2N, bool LINE_FASTEST, int LINES>

@@ -290,10 +290,10 @@ struct FilterStageOp {
   SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
     const long long i = g.idx(z, y, x);
     T v;
-    if (g.in_ring(z, y, x))
-      v = 0;
-    else if (g.written(z, y, x, 1))
+    if (g.deep(z, y, x) || (!g.in_ring(z, y, x) && g.written(z, y, x, 1)))  // (deep: the cheap common case)
       v = T(0.25) * (-in[i + st] - in[i - st] + T(2) * in[i]);
+    else if (g.in_ring(z, y, x))
+      v = 0;
     else
       v = first ? out[i] : in[i];
     out[i] = v;
