@@ -200,6 +200,139 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Vectorised 3D variant: a thread owns FOUR consecutive x cells of one (y, x) column group and marches
+// over z; all neighbour planes come in as 16-byte loads (rows are 16-byte aligned when mx % 4 == 0),
+// only the two x-neighbours outside the group are scalar.  Same masks, same arithmetic, same
+// reduction as sb_velocity_kernel.
+template <typename T>
+struct SbVec4;
+template <>
+struct alignas(16) SbVec4<float> {
+  float v[4];
+};
+template <>
+struct alignas(32) SbVec4<double> {
+  double v[4];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sb_velocity_vec4_kernel(SbGeom g, T* __restrict__ u, const T* __restrict__ psi, T p, T u0, T u1, T u2,
+                            T* __restrict__ forcing, void* max_out, int zchunk) {
+  using V = SbVec4<T>;
+  const int mx4 = g.mx >> 2;
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (y, x4) flattened
+  const int zb = blockIdx.y * zchunk;
+  const int ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
+  double vmax = -1.0e300;
+  if (gidx < (long long)g.my * mx4) {
+    const int y = (int)(gidx / mx4);
+    const int x0 = (int)(gidx - (long long)y * mx4) << 2;
+    const int gs = g.gs, w = gs + 1;
+    const bool ys = (y == gs) || (y == g.my - gs - 1);
+    const bool yi = y > gs && y < g.my - gs - 1;
+    const bool yfull = y >= 1 && y < g.my - 1;
+    const bool ring_y = (g.phys[2] && y < w) || (g.phys[3] && y >= g.my - w);
+    const bool int_y = y >= gs && y < g.my - gs;
+    // per-lane (x) masks, bit l = cell x0 + l
+    unsigned mA = 0, mB = 0, mC = 0, ringx = 0, intx = 0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int x = x0 + l;
+      const bool xs = (x == gs) || (x == g.mx - gs - 1);
+      const bool xi = x > gs && x < g.mx - gs - 1;
+      if ((xs && yfull) || (xi && ys)) mA |= 1u << l;
+      if (xi && yi) mB |= 1u << l;
+      if (yi && x >= 1 && x < g.mx - 1) mC |= 1u << l;
+      if (ring_y || (g.phys[4] && x < w) || (g.phys[5] && x >= g.mx - w)) ringx |= 1u << l;
+      if (int_y && x >= gs && x < g.mx - gs) intx |= 1u << l;
+    }
+    const long long n = g.vol, sy = g.mx, sz = g.plane;
+    const T fsv[3] = {u0, u1, u2};
+    long long i = (long long)zb * g.plane + (long long)y * g.mx + x0;
+    for (int z = zb; z < ze; ++z, i += sz) {
+      const bool zfull = z >= 1 && z < g.mz - 1;
+      const bool zin = z >= gs && z < g.mz - gs;
+      const bool zi = z > gs && z < g.mz - gs - 1;
+      const bool ringz = (g.phys[0] && z < w) || (g.phys[1] && z >= g.mz - w);
+      const unsigned ring = ringz ? 0xFu : ringx;
+      const unsigned wr = (zfull ? mA : 0u) | (zin ? mB : 0u) | (zi ? mC : 0u);
+      const unsigned calc = wr & ~ring;          // cells that get the curl
+      const unsigned keep = ~(wr | ring) & 0xFu;  // cells that keep their old value (+ free stream)
+      T c[3][4];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) c[k][l] = T(0);
+      if (calc) {
+        // a computed cell has 1 <= y < my-1 and 1 <= z < mz-1: the y / z neighbour rows exist
+        const T* fx = psi;
+        const T* fy = psi + n;
+        const T* fz = psi + 2 * n;
+        const V fz_yp = *reinterpret_cast<const V*>(fz + i + sy), fz_ym = *reinterpret_cast<const V*>(fz + i - sy);
+        const V fy_zp = *reinterpret_cast<const V*>(fy + i + sz), fy_zm = *reinterpret_cast<const V*>(fy + i - sz);
+        const V fx_zp = *reinterpret_cast<const V*>(fx + i + sz), fx_zm = *reinterpret_cast<const V*>(fx + i - sz);
+        const V fx_yp = *reinterpret_cast<const V*>(fx + i + sy), fx_ym = *reinterpret_cast<const V*>(fx + i - sy);
+        const V fz_c = *reinterpret_cast<const V*>(fz + i), fy_c = *reinterpret_cast<const V*>(fy + i);
+        // x neighbours: lanes 1..2 from the centre vectors, the outer two scalar (guarded at the row ends)
+        T fz_row[6], fy_row[6];
+        fz_row[0] = x0 > 0 ? fz[i - 1] : T(0);
+        fy_row[0] = x0 > 0 ? fy[i - 1] : T(0);
+        fz_row[5] = x0 + 4 < g.mx ? fz[i + 4] : T(0);
+        fy_row[5] = x0 + 4 < g.mx ? fy[i + 4] : T(0);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          fz_row[l + 1] = fz_c.v[l];
+          fy_row[l + 1] = fy_c.v[l];
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          if (calc & (1u << l)) {
+            c[0][l] = p * (fz_yp.v[l] - fz_ym.v[l] - fy_zp.v[l] + fy_zm.v[l]);
+            c[1][l] = p * (fx_zp.v[l] - fx_zm.v[l] - fz_row[l + 2] + fz_row[l]);
+            c[2][l] = p * (fy_row[l + 2] - fy_row[l] - fx_yp.v[l] + fx_ym.v[l]);
+          }
+        }
+      }
+      if (keep) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const V old = *reinterpret_cast<const V*>(u + i + k * n);
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            if (keep & (1u << l)) c[k][l] = old.v[l];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        V o;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) o.v[l] = c[k][l] = c[k][l] + fsv[k];
+        *reinterpret_cast<V*>(u + i + k * n) = o;
+        if (forcing) {
+          V zero;
+#pragma unroll
+          for (int l = 0; l < 4; ++l) zero.v[l] = T(0);
+          *reinterpret_cast<V*>(forcing + i + k * n) = zero;
+        }
+      }
+      if (zin) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          if (intx & (1u << l)) {
+            const T s = fabs(c[0][l]) + fabs(c[1][l]) + fabs(c[2][l]);
+            vmax = (double)s > vmax ? (double)s : vmax;
+          }
+        }
+      }
+    }
+  }
+  if (max_out) {
+    vmax = sb_block_reduce<true>(vmax);
+    if (threadIdx.x == 0) atomicMax((unsigned long long*)max_out, sb_key_from_double(vmax));
+  }
+}
+
 extern "C" int sb200_velocity_from_stream_function(const sb200_grid_t* gr, void* velocity,
                                                    const void* stream_func, double prefactor,
                                                    const double* free_stream, void* forcing, void* max_out,
@@ -217,7 +350,21 @@ extern "C" int sb200_velocity_from_stream_function(const sb200_grid_t* gr, void*
   const int zchunk = g.mz >= 64 ? 16 : (g.mz >= 16 ? 8 : g.mz);
   dim3 block(256);
   dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)((g.mz + zchunk - 1) / zchunk));
-  if (gr->dtype == SB200_F32) {
+  const size_t esz = gr->dtype == SB200_F32 ? 4 : 8;
+  const bool aligned = (((uintptr_t)velocity | (uintptr_t)stream_func | (uintptr_t)forcing) % (4 * esz)) == 0;
+  if (g.dim == 3 && g.mx % 4 == 0 && aligned) {
+    // four x cells per thread, 16-byte (float) / 32-byte (double) accesses
+    dim3 grid4((unsigned)(((long long)g.my * (g.mx / 4) + 255) / 256), grid.y);
+    if (gr->dtype == SB200_F32) {
+      SB_LAUNCH_COOP(sb_velocity_vec4_kernel<float>, grid4, block, 0, stream, g, (float*)velocity,
+                     (const float*)stream_func, (float)prefactor, (float)fs[0], (float)fs[1], (float)fs[2],
+                     (float*)forcing, max_out, zchunk);
+    } else {
+      SB_LAUNCH_COOP(sb_velocity_vec4_kernel<double>, grid4, block, 0, stream, g, (double*)velocity,
+                     (const double*)stream_func, prefactor, fs[0], fs[1], fs[2], (double*)forcing, max_out,
+                     zchunk);
+    }
+  } else if (gr->dtype == SB200_F32) {
     SB_LAUNCH_COOP(sb_velocity_kernel<float>, grid, block, 0, stream, g, (float*)velocity,
                    (const float*)stream_func, (float)prefactor, (float)fs[0], (float)fs[1], (float)fs[2],
                    (float*)forcing, max_out, zchunk);

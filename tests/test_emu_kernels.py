@@ -149,6 +149,33 @@ def test_reductions_and_fused_velocity(setup3d):
 
 
 @pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("phys", [(1,) * 6, (0, 0, 1, 1, 1, 1), (0, 1, 1, 1, 1, 1)], ids=["single", "inner", "last"])
+def test_vectorised_velocity_kernel(real_t, phys):
+    """Rows of a multiple of 4 cells take the 4-cells-per-thread kernel: same curl / ring / free stream /
+    forcing reset / max as the composed oracle, including cells that keep their old value on slab faces."""
+    rng = np.random.default_rng(9)
+    n, gs = (10, 7, 12), 2
+    shape = tuple(v + 2 * gs for v in n)
+    assert shape[2] % 4 == 0
+    g = _lib.make_grid(3, real_t, gs, n, phys)
+    psi = rng.uniform(size=(3,) + shape).astype(real_t)
+    u0 = rng.uniform(size=(3,) + shape).astype(real_t)
+    u1 = u0.copy()
+    st.curl_mpi(u0, psi, 0.8, gs, phys)
+    fs = np.array([1.0, 0.5, -0.25])
+    for c in range(3):
+        u0[c] += real_t(fs[c])
+    forcing = rng.uniform(size=(3,) + shape).astype(real_t)
+    out = np.zeros(1, np.float64)
+    call("sb200_velocity_from_stream_function", ctypes.byref(g), ptr(u1), ptr(psi), 0.8,
+         fs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ptr(forcing), ptr(out), None)
+    assert _rel(u1, u0) < _tol(real_t)
+    assert np.abs(forcing).max() == 0
+    inner = (slice(None),) + (slice(gs, -gs),) * 3
+    assert np.isclose(out[0], np.abs(u0[inner]).sum(axis=0).max(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
 def test_2d_operators(real_t):
     rng = np.random.default_rng(5)
     n, gs = (10, 14), 2
