@@ -460,7 +460,7 @@ def count_launches(sim, interactor, u_inf):
     lib = _lib.load()
     counts = {"n": 0}
     per_call = {"sb200_diffusion_timestep": 6, "sb200_laplacian_filter": 12, "sb200_penalise_field_boundary": 2,
-                "sb200_poisson_solve": 15, "sb200_velocity_from_stream_function": 2, "sb200_max_abs_sum": 2}
+                "sb200_poisson_solve": 5, "sb200_poisson_slab_spectral": 3, "sb200_velocity_from_stream_function": 2, "sb200_max_abs_sum": 2}
     originals = {}
     for fname in _lib.PROTOTYPES:
         fn = getattr(lib, fname)

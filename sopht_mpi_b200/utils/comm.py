@@ -398,6 +398,14 @@ class MPILagrangianFieldCommunicator:
         return self.rank_map[tuple(coords)]
 
     def map_lagrangian_nodes_based_on_position(self, global_lag_positions):
+        # a body that did not move keeps its ownership map (same positions -> same integers): one
+        # array comparison on the master instead of the mapping and its broadcast
+        if self.mpi_construct.size == 1 and getattr(self, "_last_positions", None) is not None:
+            if (self._last_positions.shape == np.shape(global_lag_positions)
+                    and np.array_equal(self._last_positions, global_lag_positions)):
+                return
+        if self.mpi_construct.size == 1:
+            self._last_positions = np.array(global_lag_positions, copy=True)
         if self.rank == self.master_rank:
             if global_lag_positions.shape[0] != self.grid_dim:
                 logger.error(f"global_lag_positions needs to be shape ({self.grid_dim}, ...)")
