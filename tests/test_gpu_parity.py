@@ -453,6 +453,70 @@ def test_passive_flows_against_oracle(cuda, flow_type):
     assert _rel(np.asarray(getattr(sim, name))[inner], getattr(ora, name)[inner]) <= 1e-10
 
 
+def test_poisson_stage_profiling(cuda):
+    """sb200_poisson_set_profiling / _last_stage_ms: five positive per-kernel times that add up to
+    about the solve, and a loud error when no profiled solve exists."""
+    from sopht_mpi_b200 import _lib
+    from sopht_mpi_b200.numeric.eulerian_grid_ops import UnboundedPoissonSolverMPI3D
+
+    n, gs, real_t = (64, 64, 64), 2, np.float32
+    mc, _ = _constructs(3, n, real_t)
+    solver = UnboundedPoissonSolverMPI3D(*n, mpi_construct=mc, ghost_size=gs, x_range=1.0, real_t=real_t)
+    assert solver.backend == "fft"
+    rhs = torch.rand((3,) + tuple(v + 2 * gs for v in n), device=cuda)
+    sol = torch.zeros_like(rhs)
+    solver.set_profiling(True)
+    with pytest.raises(_lib.SophtB200Error):
+        solver.last_stage_ms()
+    solver.vector_field_solve(solution_vector_field=sol, rhs_vector_field=rhs)
+    ms = solver.last_stage_ms()
+    assert list(ms) == list(solver.STAGE_NAMES) and all(v > 0 for v in ms.values())
+    solver.set_profiling(False)
+    ref = torch.zeros_like(rhs)
+    solver.vector_field_solve(solution_vector_field=ref, rhs_vector_field=rhs)
+    assert torch.equal(ref, sol)  # profiling does not change the result
+
+
+def test_full_size_step_symmetry_and_free_stream(cuda):
+    """256^3 float32 (BASELINE configs[1]): size-independent properties of the whole time step.
+    A vortex ring centred in the box stays mirror-symmetric in x and y (omega_z only picks up the
+    four-fold discretisation error of a 6-cell core); a uniform free stream with no vorticity is a
+    fixed point of the step."""
+    import bench
+    from sopht_mpi_b200.simulator import UnboundedFlowSimulator3D
+
+    n, real_t = (256, 256, 256), np.float32
+    sim = UnboundedFlowSimulator3D(grid_size=n, x_range=1.0, kinematic_viscosity=1e-3, flow_type="navier_stokes",
+                                   real_t=real_t)
+    x = sim.local_x[None, None, :].astype(np.float64)
+    y = sim.local_y[None, :, None].astype(np.float64)
+    z = sim.local_z[:, None, None].astype(np.float64)
+    sim.vorticity_field[...] = torch.from_numpy(bench.vortex_ring(x, y, z, real_t)).to(cuda)
+    sim.compute_flow_velocity(free_stream_velocity=[0.0, 0.0, 0.0])
+    for _ in range(2):
+        dt = sim.compute_stable_timestep()
+        assert 0 < dt < 1
+        sim.time_step(dt=dt, free_stream_velocity=[0.0, 0.0, 0.0])
+    w = sim.vorticity_field.tensor
+    assert torch.isfinite(w).all()
+    scale = w.abs().max().item()
+    assert w[2].abs().max().item() <= 0.1 * scale             # axial vorticity: discretisation error only
+    assert (w[1] + w[1].flip(2)).abs().max().item() <= 2e-4 * scale   # omega_y odd under x -> 1 - x
+    assert (w[0] + w[0].flip(1)).abs().max().item() <= 2e-4 * scale   # omega_x odd under y -> 1 - y
+    u = sim.velocity_field.tensor
+    assert (u[2] - u[2].flip(2)).abs().max().item() <= 2e-4 * u.abs().max().item()  # u_z even in x
+
+    sim2 = UnboundedFlowSimulator3D(grid_size=(64, 64, 128), x_range=1.0, kinematic_viscosity=1e-3,
+                                    flow_type="navier_stokes_with_forcing", real_t=real_t,
+                                    with_free_stream_flow=True)
+    u_inf = [1.0, -0.5, 0.25]
+    sim2.compute_flow_velocity(free_stream_velocity=u_inf)
+    sim2.time_step(dt=sim2.compute_stable_timestep(), free_stream_velocity=u_inf)
+    assert float(sim2.vorticity_field.tensor.abs().max()) == 0.0
+    for c in range(3):
+        assert torch.all(sim2.velocity_field.tensor[c] == real_t(u_inf[c]))
+
+
 def test_full_size_poisson_properties(cuda):
     """256^3 float32 (BASELINE config 2 size): linearity and -lap(psi) = omega in the
     interior for a smooth compact source (size-independent checks)."""
