@@ -19,8 +19,28 @@ import time
 
 import numpy as np
 
-# stdout carries ONE JSON line: NCCL's banner / warnings go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr so that
+# anything the libraries print (NCCL's version banner, ...) stays out of it; emit() restores it
+_STDOUT_FD = None
+
+
+def capture_stdout():
+    """Called by main() only (importing this module must not touch the descriptors)."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _STDOUT_FD is not None:
+        os.dup2(2, 1)
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -185,7 +205,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------- own arm
@@ -201,6 +221,7 @@ def main():
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--poisson-backend", type=str, default="auto")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -441,7 +462,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         # release the CUDA-IPC mappings of the other ranks' exchange buffers before any rank exits
         import gc

@@ -175,6 +175,11 @@ class UnboundedFlowSimulator3D:
         self._vorticity_alt = None
         self._max_abs_vel_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._max_abs_vel_version = None
+        # global max |u| of the last fused velocity sweep, reduced over the ranks and copied to pinned
+        # host memory right behind the sweep (read by the next compute_stable_timestep)
+        self._max_abs_vel_glob = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._max_abs_vel_host = torch.zeros(1, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+        self._max_abs_vel_event = torch.cuda.Event() if torch.cuda.is_available() else None
         self._reduce_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
 
     def compile_kernels(self):
@@ -339,6 +344,21 @@ class UnboundedFlowSimulator3D:
                  dptr(self.stream_func_field.tensor), float(self.real_t(0.5 / self.dx)), fs,
                  dptr(forcing), dptr(self._max_abs_vel_dev), ctx.stream())
         self._max_abs_vel_version = self.velocity_field.version
+        self._publish_max_abs_vel()
+
+    def _publish_max_abs_vel(self):
+        """Reduce max |u| over the ranks and start its copy to the host behind the producing kernel, so
+        that the next compute_stable_timestep only waits for an event.  dt = min over ranks of a
+        decreasing function of the local maximum = that function of the global maximum: one NCCL
+        all-reduce (MAX) of the device scalar replaces the reference's host allreduce(MIN) of dt
+        (flow_simulators_mpi_3d.py:447-448)."""
+        self._max_abs_vel_glob.copy_(self._max_abs_vel_dev)
+        if self._ctx.distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._max_abs_vel_glob, op=dist.ReduceOp.MAX)
+        self._max_abs_vel_host.copy_(self._max_abs_vel_glob, non_blocking=True)
+        self._max_abs_vel_event.record()
 
     def rotational_form_navier_stokes_timestep(self, dt, free_stream_velocity=None,
                                                _reset_forcing=False):
@@ -411,16 +431,9 @@ class UnboundedFlowSimulator3D:
             ctx.call("sb200_max_abs_sum", ctx.gref, dptr(self.velocity_field.tensor), self.grid_dim,
                      dptr(self._max_abs_vel_dev), ctx.stream())
             # (not cached: only the fused velocity sweep knows that it was the last writer)
-        max_dev = self._max_abs_vel_dev
-        if self._ctx.distributed:
-            # dt = min over ranks of a decreasing function of the local maximum = that function of the
-            # global maximum: one NCCL all-reduce of the device scalar replaces the reference's host
-            # allreduce(MIN) (flow_simulators_mpi_3d.py:447-448) and its host round trip per rank
-            import torch.distributed as dist
-
-            max_dev = self._max_abs_vel_dev.clone()
-            dist.all_reduce(max_dev, op=dist.ReduceOp.MAX)
-        max_vel = self.real_t(float(max_dev.item()))
+            self._publish_max_abs_vel()
+        self._max_abs_vel_event.synchronize()
+        max_vel = self.real_t(float(self._max_abs_vel_host[0]))
         dt = min(
             self.CFL * self.dx / (max_vel + tol),
             0.9 * self.dx ** 2 / (2 * self.grid_dim) / (self.kinematic_viscosity + tol),
