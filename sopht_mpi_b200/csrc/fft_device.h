@@ -527,3 +527,147 @@ SB_D void sb_fft_inverse_c(C2<T> (&v)[SB_FFT_R], int t, const C2<T>* __restrict_
 #pragma unroll
   for (int p = 0; p < SB_FFT_R; ++p) v[p].y = -v[p].y;
 }
+
+// =========================================================================================
+// 32 points per thread: n = 32 * m with m in {8, 16, 32} is ONE radix-32 stage, ONE shared-memory
+// exchange and one radix-m stage (the 16-point variant above needs two exchanges for n >= 512).
+// Half the shared-memory traffic and barriers per transform for the same FP32 work; the price is
+// 64 data registers per thread (<= 128 registers, half the resident threads).  Lines are
+// interleaved element-major (LINES per block) like the LINE_FASTEST layout above; element e sits at
+// padded position e + (e >> 5), which keeps the radix-32 scatter (thread stride 33) and the re-read
+// (unit thread stride) conflict-free for 64-bit accesses.
+#define SB_FFT_P32 32
+
+template <typename T>
+SB_D void dft32(C2<T>* a) {
+  // 32 = 2 x 16: E = DFT16(even), O = DFT16(odd), X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k]
+  C2<T> e[16], o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    e[k] = a[2 * k];
+    o[k] = a[2 * k + 1];
+  }
+  dft_small<T, 16>(e);
+  dft_small<T, 16>(o);
+  constexpr double c[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                            0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                            0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
+                            -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                            -0.92387953251128675613, -0.98078528040323044913};
+  constexpr double sn[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                             0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
+                             0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
+                             0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                             0.38268343236508977173, 0.19509032201612826785};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    C2<T> w;
+    if (k == 0)
+      w = o[0];
+    else if (k == 8)
+      w = cmul_mi(o[8]);
+    else
+      w = cmul(o[k], C2<T>{T(c[k]), T(-sn[k])});
+    a[k] = cadd(e[k], w);
+    a[k + 16] = csub(e[k], w);
+  }
+}
+
+template <typename T, int R>
+SB_D void dft_small32(C2<T>* a) {
+  if constexpr (R == 32)
+    dft32<T>(a);
+  else
+    dft_small<T, R>(a);
+}
+
+// twiddles w^1 .. w^(R-1) from the log2(R) base values w^1, w^2, w^4, (w^8, w^16)
+template <typename T, int R>
+SB_D void sb_twiddle_apply_base32(C2<T>* a, const C2<T>* pw) {
+  if constexpr (R <= 16) {
+    sb_twiddle_apply_base<T, R>(a, pw);
+  } else {
+    C2<T> w[16];  // w^0 .. w^15 (w[0] unused)
+    w[1] = pw[0];
+    w[2] = pw[1];
+    w[3] = cmul(w[1], w[2]);
+    w[4] = pw[2];
+    w[5] = cmul(w[1], w[4]);
+    w[6] = cmul(w[2], w[4]);
+    w[7] = cmul(w[3], w[4]);
+    w[8] = pw[3];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) w[8 + i] = cmul(w[i], w[8]);
+    const C2<T> w16 = pw[4];
+    a[16] = cmul(a[16], w16);
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+      a[i] = cmul(a[i], w[i]);
+      a[16 + i] = cmul(a[16 + i], cmul(w[i], w16));
+    }
+  }
+}
+
+template <int LOG2N>
+struct SbFft32C {
+  static constexpr int n = 1 << LOG2N;
+  static constexpr int Tn = n / SB_FFT_P32;          // threads per line
+  static constexpr int R2 = n / SB_FFT_P32;          // radix of the second stage (8, 16 or 32)
+  static constexpr int M = SB_FFT_P32 / R2;          // second-stage butterflies per thread
+  static constexpr int NB = R2 == 32 ? 5 : R2 == 16 ? 4 : 3;  // base twiddles per butterfly
+  static constexpr int npad = n + (n >> 5) + 1;
+  static_assert(LOG2N >= 8 && LOG2N <= 10, "32-point-per-thread transforms: n = 256, 512, 1024");
+};
+
+// forward transform of the line held in v[] (v[p] <-> element t + p Tn on entry and on return);
+// sl = padded element 0 of this thread's line, lines interleaved LINES-wide
+template <typename T, int LOG2N, int LINES>
+SB_D void sb_fft32_forward_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+  using P = SbFft32C<LOG2N>;
+  dft32<T>(v);
+  {
+    C2<T>* dst = sl + (33 * t) * LINES;  // position 32 t + q, padded 33 t + q
+#pragma unroll
+    for (int q = 0; q < SB_FFT_P32; ++q) dst[q * LINES] = v[q];
+  }
+  // base twiddles of the second stage, in flight across the exchange (the data registers are dead)
+  C2<T> pw[P::M * P::NB];
+#pragma unroll
+  for (int m = 0; m < P::M; ++m) {
+    const int k = t + m * P::Tn;  // butterfly index j < 32 = Ns, twiddle W_n^(k q)
+#pragma unroll
+    for (int b = 0; b < P::NB; ++b) pw[m * P::NB + b] = tw[k << b];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < SB_FFT_P32; ++p) {
+    // element t + p Tn; its padding (e >> 5) does not depend on t because t < Tn <= 32
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int pad = (p * P::Tn) >> 5;
+    v[p] = sl[(t + p * P::Tn + pad) * LINES];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < P::M; ++m) {
+    C2<T> a[P::R2];
+#pragma unroll
+    for (int q = 0; q < P::R2; ++q) a[q] = v[m + P::M * q];
+    sb_twiddle_apply_base32<T, P::R2>(a, pw + m * P::NB);
+    dft_small32<T, P::R2>(a);
+#pragma unroll
+    for (int q = 0; q < P::R2; ++q) v[m + P::M * q] = a[q];
+  }
+}
+
+template <typename T, int LOG2N, int LINES>
+SB_D void sb_fft32_inverse_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+l"(tw));  // see sb_fft_inverse_c
+#endif
+#pragma unroll
+  for (int p = 0; p < SB_FFT_P32; ++p) v[p].y = -v[p].y;
+  sb_fft32_forward_c<T, LOG2N, LINES>(v, t, tw, sl);
+#pragma unroll
+  for (int p = 0; p < SB_FFT_P32; ++p) v[p].y = -v[p].y;
+}

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <vector>
 
+
 #ifndef SB200_EMU
 #define SB_DEV_ALLOC(ptr, bytes) (cudaMalloc((void**)&(ptr), (bytes)) == cudaSuccess)
 #define SB_DEV_FREE(ptr) cudaFree(ptr)
@@ -49,6 +50,12 @@ struct SbLines {
   }
   SB_HD long long point(int t, int p, int Tn) const {
     return (long long)(p >> qs) * bstride + (long long)(t + (p & ((1 << qs) - 1)) * Tn) * pt;
+  }
+  // the same line seen by n / 32 threads of 32 points: point k = t + p Tn32 with Tn32 = Tn16 / 2, so
+  // a block of 2^qs sixteen-point slots holds 2^(qs+1) of these
+  SB_HD long long point32(int t, int p, int Tn) const {
+    const int q = qs + 1;
+    return (long long)(p >> q) * bstride + (long long)(t + (p & ((1 << q) - 1)) * Tn) * pt;
   }
 };
 
@@ -391,6 +398,112 @@ __global__ void __launch_bounds__(sb_lb_threads(LOG2N, LINES), MODE == 1 ? sb_lb
   }
 }
 
+// ---------------------------------------------------------------- strided pass, 32 points per thread
+// Same passes (MODE 0 / 1 / 2) for n = 512 and 1024 with ONE shared-memory exchange per transform
+// (fft_device.h, sb_fft32_*): a line is n / 32 threads, a block 8 lines.  VARIANT as above
+// (bit 0 blocked point addressing, bit 1 thread-order Green's table with 32 factors per thread).
+constexpr int sb_p32_min_blocks(int mode, int log2n, int lines) {
+  const int nt = lines * ((1 << log2n) / SB_FFT_P32);
+  if (mode == 2 && log2n == 9) return 768 / nt;  // the inverse-only pass fits 80 registers
+  return 512 / nt > 0 ? 512 / nt : 1;            // <= 128 registers per thread
+}
+
+template <typename T, int MODE, int LOG2N, int LINES, int VARIANT>
+__global__ void __launch_bounds__(LINES*((1 << LOG2N) / SB_FFT_P32), sb_p32_min_blocks(MODE, LOG2N, LINES))
+    sb_fft_strided32_kernel(const C2<T>* in, SbLines lin, C2<T>* out, SbLines lout,
+                            const C2<T>* __restrict__ tw, SbGreensTable<T> gt) {
+  SB_DYN_SMEM(smem_raw);
+  using FC = SbFft32C<LOG2N>;
+  constexpr int PT = SB_FFT_P32, Tn = FC::Tn, NT = LINES * Tn;
+  constexpr int LINES_SHIFT = LINES == 16 ? 4 : LINES == 8 ? 3 : LINES == 4 ? 2 : LINES == 2 ? 1 : 0;
+  constexpr bool BLOCKED = (VARIANT & 1) != 0;
+  constexpr bool G2 = (VARIANT & 2) != 0;
+  static_assert(!G2 || (MODE == 1 && sizeof(T) == 4), "thread-order table: fused float kernel");
+  constexpr int IN = (MODE == 0 || MODE == 1) ? PT / 2 : PT;
+  constexpr int OUT = (MODE == 1 || MODE == 2) ? PT / 2 : PT;
+  C2<T>* sm = reinterpret_cast<C2<T>*>(smem_raw);
+  const int l = threadIdx.x & (LINES - 1), t = threadIdx.x >> LINES_SHIFT;
+  const int ib = G2 ? blockIdx.y : blockIdx.x;
+  const int i = (ib << LINES_SHIFT) + l;
+  const int o1 = G2 ? blockIdx.z : blockIdx.y, o2 = G2 ? blockIdx.x : blockIdx.z;
+  const bool valid = i < lin.inner;
+  const int ic = valid ? i : lin.inner - 1;
+  C2<T>* sline = sm + l;
+  float4* gstage = nullptr;
+  if constexpr (G2) {
+    gstage = reinterpret_cast<float4*>(sm + LINES * FC::npad) + threadIdx.x;
+    const int g1 = o1 + gt.o1_off;
+    const int m1 = g1 <= (gt.n1_full >> 1) ? g1 : gt.n1_full - g1;
+    const float4* src = reinterpret_cast<const float4*>(gt.g2) +
+                        (((long long)m1 * gridDim.y + ib) * NT + threadIdx.x) * (PT / 4);
+#pragma unroll
+    for (int k = 0; k < PT / 4; ++k) sb_cp_async16(gstage + k * NT, src + k);
+  }
+  C2<T> v[PT];
+  {
+    const C2<T>* gp = in + lin.base(ic, o1, o2);
+    if constexpr (BLOCKED) {
+#pragma unroll
+      for (int p = 0; p < PT; ++p) v[p] = p < IN ? gp[lin.point32(t, p, Tn)] : C2<T>{T(0), T(0)};
+    } else {
+      const long long sp = (long long)Tn * lin.pt;
+      gp += (long long)t * lin.pt;
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        if (p < IN) {
+          v[p] = *gp;
+          gp += sp;
+        } else {
+          v[p] = C2<T>{T(0), T(0)};
+        }
+      }
+    }
+  }
+  if constexpr (MODE != 2) sb_fft32_forward_c<T, LOG2N, LINES>(v, t, tw, sline);
+  if constexpr (G2) {
+    sb_cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < PT / 4; ++k) {
+      const float4 gv = gstage[k * NT];
+      v[4 * k] = cscale(v[4 * k], gv.x);
+      v[4 * k + 1] = cscale(v[4 * k + 1], gv.y);
+      v[4 * k + 2] = cscale(v[4 * k + 2], gv.z);
+      v[4 * k + 3] = cscale(v[4 * k + 3], gv.w);
+    }
+  } else if constexpr (MODE == 1) {
+    const int g1 = o1 + gt.o1_off;
+    const int m1 = g1 <= (gt.n1_full >> 1) ? g1 : gt.n1_full - g1;
+    const int kxg = ic + gt.kx0 < gt.kx_last ? ic + gt.kx0 : gt.kx_last;
+    const T* g = gt.g + ((long long)m1 * gt.g_s1 + kxg);
+    const long long gs = (long long)Tn * gt.g_pt;
+    const T* ga = g + (long long)t * gt.g_pt;
+    const T* gb = g + (long long)(FC::n - t - (PT / 2) * Tn) * gt.g_pt;
+#pragma unroll
+    for (int p = 0; p < PT / 2; ++p) {
+      v[p] = cscale(v[p], *ga);
+      v[p + PT / 2] = cscale(v[p + PT / 2], *gb);
+      ga += gs;
+      gb -= gs;
+    }
+  }
+  if constexpr (MODE == 1 || MODE == 2) sb_fft32_inverse_c<T, LOG2N, LINES>(v, t, tw, sline);
+  if (valid) {
+    C2<T>* gp = out + lout.base(i, o1, o2);
+    if constexpr (BLOCKED) {
+#pragma unroll
+      for (int p = 0; p < OUT; ++p) gp[lout.point32(t, p, Tn)] = v[p];
+    } else {
+      const long long sp = (long long)Tn * lout.pt;
+      gp += (long long)t * lout.pt;
+#pragma unroll
+      for (int p = 0; p < OUT; ++p) {
+        *gp = v[p];
+        gp += sp;
+      }
+    }
+  }
+}
+
 // Re(spectrum) * scale -> mirror-compressed table
 template <typename T>
 struct GreensExtractOp {
@@ -414,9 +527,10 @@ struct GreensThreadOrderOp {
   long long g_pt, g_s1;
   int n, Tn, lines, nib, pitch;
   int kx0, inner;  // first global kx of this rank's lines, number of lines
+  int pt;          // bins per thread (16 or 32)
   SB_D void operator()(long long idx) const {
-    const int p = (int)(idx & 15);
-    long long r = idx >> 4;
+    const int p = (int)(idx % pt);
+    long long r = idx / pt;
     const int l = (int)(r % lines);
     r /= lines;
     const int t = (int)(r % Tn);
@@ -544,10 +658,57 @@ static int launch_x_c2r(const SbFftPlan& plan, int ny, int nz, int ncomp, const 
   return launch_x_c2r_c<T, 0>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
 }
 
+// 32 points per thread (one exchange per transform) for n = 512 / 1024 in float; SB200_FFT_P32 is a
+// developer knob: bit m set = use it for MODE m (default below = what measured fastest on B200)
+static inline bool sb_use_p32(int mode, int log2n) {
+  // measured (profiles/r01_fft_tuning.md): n = 1024 all three passes, n = 512 the forward and the fused pass
+  static const int env = getenv("SB200_FFT_P32") ? atoi(getenv("SB200_FFT_P32")) : -1;
+  const int mask = env >= 0 ? env : (log2n == 10 ? 7 : 3);
+  return (log2n == 9 || log2n == 10) && mode >= 0 && mode <= 2 && ((mask >> mode) & 1);
+}
+
+template <typename T, int MODE, int LOG2N>
+static int launch_strided32(const C2<T>* in, const SbLines& lin, C2<T>* out, const SbLines& lout,
+                            const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
+  constexpr int LINES = 8, NT = LINES * ((1 << LOG2N) / SB_FFT_P32);
+  const size_t smem = sizeof(C2<T>) * (size_t)LINES * SbFft32C<LOG2N>::npad;
+  const unsigned nib = (unsigned)((lin.inner + LINES - 1) / LINES);
+  const bool blocked = !(lin.qs == 4 && lout.qs == 4);
+#define SB_LAUNCH_STRIDED32(VARIANT, GRID, SMEM)                                                   \
+  do {                                                                                             \
+    SB_KERNEL_ATTR_SMEM((sb_fft_strided32_kernel<T, MODE, LOG2N, LINES, VARIANT>), SMEM);          \
+    SB_LAUNCH_COOP((sb_fft_strided32_kernel<T, MODE, LOG2N, LINES, VARIANT>), GRID, dim3(NT), SMEM, \
+                   stream, in, lin, out, lout, tw, gt);                                            \
+  } while (0)
+  if constexpr (MODE == 1) {
+    if (gt.g2) {
+      const size_t smem2 = smem + (size_t)NT * SB_FFT_P32 * sizeof(float);
+      const dim3 grid2((unsigned)lin.n2, nib, (unsigned)lin.n1);
+      if (blocked)
+        SB_LAUNCH_STRIDED32(3, grid2, smem2);
+      else
+        SB_LAUNCH_STRIDED32(2, grid2, smem2);
+      SB_CHECK_LAUNCH("fft_strided32");
+      return 0;
+    }
+  }
+  const dim3 grid(nib, (unsigned)lin.n1, (unsigned)lin.n2);
+  if (blocked)
+    SB_LAUNCH_STRIDED32(1, grid, smem);
+  else
+    SB_LAUNCH_STRIDED32(0, grid, smem);
+#undef SB_LAUNCH_STRIDED32
+  SB_CHECK_LAUNCH("fft_strided32");
+  return 0;
+}
+
 template <typename T, int MODE, int LOG2N>
 static int launch_strided_c(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
                             const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
   constexpr int LINES = LOG2N > 0 ? sb_strided_lines<T>(LOG2N, MODE) : 0;
+  if constexpr (sizeof(T) == 4 && (LOG2N == 9 || LOG2N == 10) && MODE <= 2) {
+    if (sb_use_p32(MODE, LOG2N)) return launch_strided32<T, MODE, LOG2N>(in, lin, out, lout, tw, gt, stream);
+  }
   const int lb = LOG2N > 0 ? LINES : lines_per_block_for(plan.threads, sizeof(T), true);
   const size_t smem = (size_t)lb * sb_fft_npad(plan.n) * sizeof(C2<T>);
   int lb_shift = 0;
@@ -668,14 +829,15 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
                      stream, "greens_extract");
   if (!e && p->dim == 3 && sizeof(T) == 4 && st->pz.log2n >= 8 && st->pz.log2n <= 11) {
     // thread-order copy for the specialised fused z kernel
-    const int lines = sb_strided_lines<T>(st->pz.log2n, 1), Tn = st->pz.threads;
+    const int pt = sb_use_p32(1, st->pz.log2n) ? SB_FFT_P32 : SB_FFT_R;
+    const int lines = pt == SB_FFT_P32 ? 8 : sb_strided_lines<T>(st->pz.log2n, 1), Tn = 2 * nz / pt;
     const int inner = p->nranks > 1 ? st->kxl : nx + 1, kx0 = p->nranks > 1 ? p->rank * st->kxl : 0;
     const int nib = (inner + lines - 1) / lines;
-    const long long count = (long long)(ny + 1) * nib * Tn * lines * SB_FFT_R;
+    const long long count = (long long)(ny + 1) * nib * Tn * lines * pt;
     SB_REQUIRE(SB_DEV_ALLOC(st->G2, sizeof(T) * count), "fft backend: cannot allocate the thread-order table");
     st->bytes += sizeof(T) * count;
     e = sb_launch_flat(count, GreensThreadOrderOp<T>{st->G2, st->G, (long long)(ny + 1) * P, P, 2 * nz, Tn, lines,
-                                                     nib, (int)P, kx0, inner},
+                                                     nib, (int)P, kx0, inner, pt},
                        stream, "greens_thread_order");
   }
   SB_STREAM_SYNC(stream);
