@@ -621,7 +621,8 @@ struct SbFft32C {
 
 // forward transform of the line held in v[] (v[p] <-> element t + p Tn on entry and on return);
 // sl = padded element 0 of this thread's line, lines interleaved LINES-wide
-template <typename T, int LOG2N, int LINES>
+// TRAIL: barrier after the re-read, needed only when the exchange buffer is written again afterwards
+template <typename T, int LOG2N, int LINES, bool TRAIL = true>
 SB_D void sb_fft32_forward_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
   using P = SbFft32C<LOG2N>;
   dft32<T>(v);
@@ -642,12 +643,10 @@ SB_D void sb_fft32_forward_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restr
 #pragma unroll
   for (int p = 0; p < SB_FFT_P32; ++p) {
     // element t + p Tn; its padding (e >> 5) does not depend on t because t < Tn <= 32
-    constexpr int dummy = 0;
-    (void)dummy;
     const int pad = (p * P::Tn) >> 5;
     v[p] = sl[(t + p * P::Tn + pad) * LINES];
   }
-  __syncthreads();
+  if constexpr (TRAIL) __syncthreads();
 #pragma unroll
   for (int m = 0; m < P::M; ++m) {
     C2<T> a[P::R2];
@@ -660,14 +659,14 @@ SB_D void sb_fft32_forward_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restr
   }
 }
 
-template <typename T, int LOG2N, int LINES>
+template <typename T, int LOG2N, int LINES, bool TRAIL = true>
 SB_D void sb_fft32_inverse_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restrict__ tw, C2<T>* sl) {
 #if defined(__CUDA_ARCH__)
   asm volatile("" : "+l"(tw));  // see sb_fft_inverse_c
 #endif
 #pragma unroll
   for (int p = 0; p < SB_FFT_P32; ++p) v[p].y = -v[p].y;
-  sb_fft32_forward_c<T, LOG2N, LINES>(v, t, tw, sl);
+  sb_fft32_forward_c<T, LOG2N, LINES, TRAIL>(v, t, tw, sl);
 #pragma unroll
   for (int p = 0; p < SB_FFT_P32; ++p) v[p].y = -v[p].y;
 }

@@ -15,6 +15,9 @@
 #include <cstdlib>
 #include <vector>
 
+// lines per block of the 32-point-per-thread kernels (16 lines measured slower at n = 512)
+#define SB_P32_LINES(log2n) 8
+
 
 #ifndef SB200_EMU
 #define SB_DEV_ALLOC(ptr, bytes) (cudaMalloc((void**)&(ptr), (bytes)) == cudaSuccess)
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(LINES*((1 << LOG2N) / SB_FFT_P32), sb_p32_min_
       }
     }
   }
-  if constexpr (MODE != 2) sb_fft32_forward_c<T, LOG2N, LINES>(v, t, tw, sline);
+  if constexpr (MODE != 2) sb_fft32_forward_c<T, LOG2N, LINES, MODE == 1>(v, t, tw, sline);
   if constexpr (G2) {
     sb_cp_async_wait_all();
 #pragma unroll
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(LINES*((1 << LOG2N) / SB_FFT_P32), sb_p32_min_
       gb -= gs;
     }
   }
-  if constexpr (MODE == 1 || MODE == 2) sb_fft32_inverse_c<T, LOG2N, LINES>(v, t, tw, sline);
+  if constexpr (MODE == 1 || MODE == 2) sb_fft32_inverse_c<T, LOG2N, LINES, false>(v, t, tw, sline);
   if (valid) {
     C2<T>* gp = out + lout.base(i, o1, o2);
     if constexpr (BLOCKED) {
@@ -670,7 +673,7 @@ static inline bool sb_use_p32(int mode, int log2n) {
 template <typename T, int MODE, int LOG2N>
 static int launch_strided32(const C2<T>* in, const SbLines& lin, C2<T>* out, const SbLines& lout,
                             const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
-  constexpr int LINES = 8, NT = LINES * ((1 << LOG2N) / SB_FFT_P32);
+  constexpr int LINES = SB_P32_LINES(LOG2N), NT = LINES * ((1 << LOG2N) / SB_FFT_P32);
   const size_t smem = sizeof(C2<T>) * (size_t)LINES * SbFft32C<LOG2N>::npad;
   const unsigned nib = (unsigned)((lin.inner + LINES - 1) / LINES);
   const bool blocked = !(lin.qs == 4 && lout.qs == 4);
@@ -830,7 +833,8 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   if (!e && p->dim == 3 && sizeof(T) == 4 && st->pz.log2n >= 8 && st->pz.log2n <= 11) {
     // thread-order copy for the specialised fused z kernel
     const int pt = sb_use_p32(1, st->pz.log2n) ? SB_FFT_P32 : SB_FFT_R;
-    const int lines = pt == SB_FFT_P32 ? 8 : sb_strided_lines<T>(st->pz.log2n, 1), Tn = 2 * nz / pt;
+    const int lines = pt == SB_FFT_P32 ? SB_P32_LINES(st->pz.log2n) : sb_strided_lines<T>(st->pz.log2n, 1);
+    const int Tn = 2 * nz / pt;
     const int inner = p->nranks > 1 ? st->kxl : nx + 1, kx0 = p->nranks > 1 ? p->rank * st->kxl : 0;
     const int nib = (inner + lines - 1) / lines;
     const long long count = (long long)(ny + 1) * nib * Tn * lines * pt;
