@@ -129,9 +129,17 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(device_index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        try:
+            self.first = sum(1 for _ in open(self.path))
+        except OSError:
+            self.first = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -144,7 +152,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        lines = open(self.path).read().splitlines()
+        timed = lines[self.first:]
+        # a 40 ms timed region may see no 20 ms sample of its own: fall back to the last samples of
+        # the (>= 1 s, same workload) warm-up that precedes it
+        for line in (timed if len(timed) >= 2 else lines[-10:]):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -319,10 +331,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
+    # W warm-up steps, extended (never shortened) until the GPU has been busy for about a second: a
+    # 256^3 step is 2 ms, and three of them do not bring the SM clock up from idle.  The number of
+    # extra steps is decided on rank 0 and broadcast (the steps contain collectives).
+    n_warm = max(args.warmup, 3)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_warm = time.perf_counter()
+    for _ in range(n_warm):
+        one_step()
+    barrier()
+    per_step = max((time.perf_counter() - t_warm) / n_warm, 1e-5)
+    extra = torch.tensor([max(0, min(400, int(1.0 / per_step)) - n_warm)], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.broadcast(extra, src=0)
+    for _ in range(int(extra.item())):
+        one_step()
+    n_warm += int(extra.item())
+    barrier()
+    if sampler:
+        sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -443,7 +471,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": cells / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": name, "grid_zyx": grid, "flow_type": flow_type, "lagrangian_points": n_lag,
