@@ -50,8 +50,8 @@ UNIT = "Mcell-updates/s"
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused z kernel, from the
 # `ncu --set full` captures kept under profiles/ (r01_ncu_step256_summary.txt, r01_ncu_z512_summary.txt)
-NCU_Z_PASS_TRAFFIC_BYTES = {"vortex_ring_256_f32": 1.075759e9 + 0.760783e9,
-                            "vortex_ring_512_f32": 8.638830e9 + 6.416844e9}
+NCU_Z_PASS_TRAFFIC_BYTES = {"vortex_ring_256_f32": 1.076057e9 + 0.761642e9,
+                            "vortex_ring_512_f32": 8.638908e9 + 6.418693e9}
 
 WORKLOADS = {
     # name: (grid (z,y,x), flow_type, with immersed body)
@@ -406,7 +406,7 @@ def main():
             zk = "y_forward_z_fused_y_inverse"
         z_bytes = (8 if zk.startswith("z_") else 20) * w_bytes * 3 * local_cells
         achieved = z_bytes / (acc[zk] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "sb_fft_strided_kernel<float, MODE 1> (fused z pass of the Poisson "
+        roofline = {"bound": "hbm", "kernel": "sb_fft_strided32_kernel<float, MODE 1> (fused z pass of the Poisson "
                     "vector solve: forward FFT x Green x inverse FFT, in place)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": NCU_Z_PASS_TRAFFIC_BYTES.get(name) if world == 1 else None,
