@@ -26,9 +26,10 @@ from ...numeric.eulerian_grid_ops.ops import OpContext
 from ...utils import MPI, MPIConstruct3D, MPIGhostCommunicator3D, logger
 from ...utils.device import current_stream_ptr, dptr, zeros, zeros_like
 from ...utils.precision import get_test_tol
+from .flow_simulator_common import FlowSimulatorCommon
 
 
-class UnboundedFlowSimulator3D:
+class UnboundedFlowSimulator3D(FlowSimulatorCommon):
     """Class for the GPU 3D unbounded flow simulator"""
 
     def __init__(
@@ -77,18 +78,12 @@ class UnboundedFlowSimulator3D:
             self.penalty_zone_width = kwargs.get("penalty_zone_width", 2)
             self.with_free_stream_flow = kwargs.get("with_free_stream_flow", False)
             if self.filter_vorticity:
+                # same default as the reference when no filter_setting_dict is passed (:97-111)
+                given = kwargs.get("filter_setting_dict")
+                self.filter_setting_dict = given if given is not None else {"order": 2, "type": "multiplicative"}
                 logger.warning(
-                    "==============================================="
-                    "\nVorticity filtering is turned on.")
-                self.filter_setting_dict = kwargs.get("filter_setting_dict")
-                if self.filter_setting_dict is None:
-                    self.filter_setting_dict = {"order": 2, "type": "multiplicative"}
-                    logger.warning(
-                        "Since a dict named filter_setting with keys "
-                        "\n'order' and 'type' is not provided, setting "
-                        f"\ndefault filter order = {self.filter_setting_dict['order']}"
-                        f"\nand type: {self.filter_setting_dict['type']}")
-                logger.warning("===============================================")
+                    "vorticity filter on: order {order}, type {type}".format(**self.filter_setting_dict)
+                    + ("" if given is not None else " (defaults; pass filter_setting_dict={'order': .., 'type': ..})"))
         self.compile_kernels()
         self.finalise_flow_timestep()
 
@@ -109,38 +104,10 @@ class UnboundedFlowSimulator3D:
         self.device = self.mpi_construct.device
 
     def init_domain(self):
-        """Local domain (with ghost cells); reference :124-168."""
-        self.y_range = self.x_range * self.grid_size_y / self.grid_size_x
-        self.z_range = self.x_range * self.grid_size_z / self.grid_size_x
-        self.dx = self.real_t(self.x_range / self.grid_size_x)
-        eul_grid_shift = self.dx / 2.0
-        ghost_grid_shift = self.ghost_size * self.dx
-        local_grid_size = self.mpi_construct.local_grid_size
-        substart_idx = self.mpi_construct.grid.coords * local_grid_size
-        subend_idx = substart_idx + local_grid_size
-        substart_z, substart_y, substart_x = substart_idx * self.dx
-        subend_z, subend_y, subend_x = subend_idx * self.dx
-        nz, ny, nx = local_grid_size
-        gs = self.ghost_size
-        self.local_x = np.linspace(eul_grid_shift + substart_x - ghost_grid_shift,
-                                   subend_x - eul_grid_shift + ghost_grid_shift,
-                                   nx + 2 * gs).astype(self.real_t)
-        self.local_y = np.linspace(eul_grid_shift + substart_y - ghost_grid_shift,
-                                   subend_y - eul_grid_shift + ghost_grid_shift,
-                                   ny + 2 * gs).astype(self.real_t)
-        self.local_z = np.linspace(eul_grid_shift + substart_z - ghost_grid_shift,
-                                   subend_z - eul_grid_shift + ghost_grid_shift,
-                                   nz + 2 * gs).astype(self.real_t)
-        self.local_grid_size_with_ghost = local_grid_size + 2 * self.ghost_size
+        """Local domain (with ghost cells), reference :124-168: coordinate lines instead of the full
+        meshgrid (see ``position_field``)."""
+        self._init_local_coordinates()
         self._position_field = None
-        logger.info(
-            "==============================================="
-            f"\n{self.grid_dim}D flow domain initialized with:"
-            f"\nX axis from 0.0 to {self.x_range}"
-            f"\nY axis from 0.0 to {self.y_range}"
-            f"\nZ axis from 0.0 to {self.z_range}"
-            "\nPlease initialize bodies within these bounds!"
-            "\n===============================================")
 
     @property
     def position_field(self):
@@ -282,13 +249,6 @@ class UnboundedFlowSimulator3D:
         elif self.flow_type == "navier_stokes_with_forcing":
             self.flow_time_step = self.navier_stokes_with_forcing_timestep
 
-    def update_simulator_time(self, dt):
-        self.time += dt
-
-    def time_step(self, dt, **kwargs):
-        self.flow_time_step(dt=dt, **kwargs)
-        self.update_simulator_time(dt=dt)
-
     def scalar_advection_and_diffusion_timestep(self, dt: float, **kwargs) -> None:
         self.advection_timestep(
             field=self.primary_scalar_field,
@@ -416,11 +376,6 @@ class UnboundedFlowSimulator3D:
                                     _reset_forcing=True)
 
     # ------------------------------------------------------------ diagnostics
-    def _reduce(self, name, field, ncomp):
-        ctx = self._ctx
-        ctx.call(name, ctx.gref, dptr(field.tensor), ncomp, dptr(self._reduce_dev), ctx.stream())
-        return float(self._reduce_dev.item())
-
     def compute_stable_timestep(self, dt_prefac=1, precision="single"):
         """reference :426-449; max over interior of sum |u_i| comes from the fused velocity
         sweep when the velocity has not been touched from the host since."""

@@ -10,143 +10,106 @@ from ...utils.comm import MPI
 from .immersed_body_forcing_grid import EmptyForcingGrid
 
 
-class ImmersedBodyFlowInteractionMPI(VirtualBoundaryForcingMPI):
-    """Base class; derived classes set ``body_flow_forces``, ``body_flow_torques``,
-    ``forcing_grid`` and ``master_rank`` before calling this initialiser."""
+def _report_lagrangian_resolution(grid_name, max_lag_grid_dx, dx):
+    """One log record telling the user how the forcing-point spacing compares with the flow grid
+    (the coupling works best for spacings between dx / 2 and 2 dx)."""
+    ratio = max_lag_grid_dx / dx
+    if ratio > 2.0:
+        verdict = ("too coarse for the flow grid (more than 2 dx between forcing points): the body leaks, "
+                   "refine the Lagrangian grid")
+    elif ratio < 0.5:
+        verdict = ("finer than the flow grid needs (less than dx / 2 between forcing points): redundant "
+                   "points, coarsen the Lagrangian grid")
+    else:
+        verdict = "matched to the flow grid"
+    logger.warning(f"{grid_name}: max Lagrangian spacing {max_lag_grid_dx:.6g} = {ratio:.3g} dx "
+                   f"(dx = {dx:.6g}) is {verdict}")
 
-    def __init__(
-        self,
-        mpi_construct,
-        mpi_ghost_exchange_communicator,
-        eul_grid_forcing_field,
-        eul_grid_velocity_field,
-        virtual_boundary_stiffness_coeff,
-        virtual_boundary_damping_coeff,
-        dx,
-        grid_dim,
-        eul_grid_coord_shift=None,
-        interp_kernel_width=None,
-        enable_eul_grid_forcing_reset=False,
-        start_time=0.0,
-        assume_data_locality=False,
-        auto_ghosting=True,
-    ):
+
+class ImmersedBodyFlowInteractionMPI(VirtualBoundaryForcingMPI):
+    """Couples one body to the flow (API of the reference's ``ImmersedBodyFlowInteractionMPI``,
+    ``immersed_body_flow_interaction_mpi.py:10-202``).  Subclasses create ``forcing_grid`` (the real
+    one on ``master_rank``, an ``EmptyForcingGrid`` elsewhere), ``body_flow_forces`` and
+    ``body_flow_torques`` first.  The penalty coefficients are given per unit area (3D) / length
+    (2D) and scaled here by ``max_lag_grid_dx ** (grid_dim - 1)``."""
+
+    def __init__(self, mpi_construct, mpi_ghost_exchange_communicator, eul_grid_forcing_field,
+                 eul_grid_velocity_field, virtual_boundary_stiffness_coeff, virtual_boundary_damping_coeff,
+                 dx, grid_dim, eul_grid_coord_shift=None, interp_kernel_width=None,
+                 enable_eul_grid_forcing_reset=False, start_time=0.0, assume_data_locality=False,
+                 auto_ghosting=True):
         self.mpi_ghost_exchange_communicator = mpi_ghost_exchange_communicator
+        self.auto_ghosting = bool(auto_ghosting)
+        # views: the interactor follows whatever the simulator does to its fields
         self.eul_grid_forcing_field = eul_grid_forcing_field.view()
         self.eul_grid_velocity_field = eul_grid_velocity_field.view()
         self.eul_grid_velocity_field.flags.writeable = False
 
-        max_lag_grid_dx = self.forcing_grid.get_maximum_lagrangian_grid_spacing()
-        max_lag_grid_dx = mpi_construct.grid.bcast(max_lag_grid_dx, root=self.master_rank)
-        grid_type = type(self.forcing_grid).__name__
-        logger.warning(
-            "==========================================================\n"
-            f"For {grid_type}:")
-        if max_lag_grid_dx > 2 * dx:
-            logger.warning(
-                f"Eulerian grid spacing (dx): {dx}"
-                f"\nMax Lagrangian grid spacing: {max_lag_grid_dx} > 2 * dx"
-                "\nThe Lagrangian grid of the body is too coarse relative to"
-                "\nthe Eulerian grid of the flow, which can lead to unexpected"
-                "\nconvergence. Please make the Lagrangian grid finer.")
-        elif max_lag_grid_dx < 0.5 * dx:
-            logger.warning(
-                "==========================================================\n"
-                f"Eulerian grid spacing (dx): {dx}"
-                f"\nMax Lagrangian grid spacing: {max_lag_grid_dx} < 0.5 * dx"
-                "\nThe Lagrangian grid of the body is too fine relative to"
-                "\nthe Eulerian grid of the flow, which corresponds to redundant"
-                "\nforcing points. Please make the Lagrangian grid coarser.")
-        else:
-            logger.warning(
-                "Lagrangian grid is resolved almost the same as the Eulerian"
-                "\ngrid of the flow.")
-        logger.warning("==========================================================")
+        spacing = mpi_construct.grid.bcast(self.forcing_grid.get_maximum_lagrangian_grid_spacing(),
+                                           root=self.master_rank)
+        _report_lagrangian_resolution(type(self.forcing_grid).__name__, spacing, dx)
+        area = spacing ** (grid_dim - 1)
+        VirtualBoundaryForcingMPI.__init__(
+            self, mpi_construct=mpi_construct, ghost_size=mpi_ghost_exchange_communicator.ghost_size,
+            virtual_boundary_stiffness_coeff=virtual_boundary_stiffness_coeff * area,
+            virtual_boundary_damping_coeff=virtual_boundary_damping_coeff * area, grid_dim=grid_dim, dx=dx,
+            eul_grid_coord_shift=eul_grid_coord_shift, interp_kernel_width=interp_kernel_width,
+            enable_eul_grid_forcing_reset=enable_eul_grid_forcing_reset, start_time=start_time,
+            master_rank=self.master_rank, global_lag_grid_position_field=self.forcing_grid.position_field,
+            assume_data_locality=assume_data_locality)
+        if not self.auto_ghosting:
+            logger.warning("interactor created with auto_ghosting=False: exchange the velocity ghost cells "
+                           "yourself before every interaction")
 
-        virtual_boundary_stiffness_coeff *= max_lag_grid_dx ** (grid_dim - 1)
-        virtual_boundary_damping_coeff *= max_lag_grid_dx ** (grid_dim - 1)
-
-        super().__init__(
-            mpi_construct=mpi_construct,
-            ghost_size=self.mpi_ghost_exchange_communicator.ghost_size,
-            virtual_boundary_stiffness_coeff=virtual_boundary_stiffness_coeff,
-            virtual_boundary_damping_coeff=virtual_boundary_damping_coeff,
-            grid_dim=grid_dim,
-            dx=dx,
-            eul_grid_coord_shift=eul_grid_coord_shift,
-            interp_kernel_width=interp_kernel_width,
-            enable_eul_grid_forcing_reset=enable_eul_grid_forcing_reset,
-            start_time=start_time,
-            master_rank=self.master_rank,
-            global_lag_grid_position_field=self.forcing_grid.position_field,
-            assume_data_locality=assume_data_locality,
-        )
-
-        if auto_ghosting:
-            self.compute_full_interaction = self._compute_full_interaction_with_ghosting
-            self.compute_interaction_on_lag_grid = self._compute_interaction_on_lag_grid_with_ghosting
-        else:
-            logger.warning(
-                "==========================================================\n"
-                "Auto ghosting of velocity field is disabled for interactor.\n"
-                "Please ensure ghosting is done before calling interactor functions.\n"
-                "==========================================================")
-            self.compute_full_interaction = self._compute_full_interaction_without_ghosting
-            self.compute_interaction_on_lag_grid = self._compute_interaction_on_lag_grid_without_ghosting
-
-    def __call__(self):
-        self.compute_full_interaction()
-
-    def _ghost_velocity_field_for_interaction(self):
-        self.eul_grid_velocity_field.flags.writeable = True
-        self.mpi_ghost_exchange_communicator.exchange_vector_field_init(self.eul_grid_velocity_field)
-        self.mpi_ghost_exchange_communicator.exchange_finalise()
-        self.eul_grid_velocity_field.flags.writeable = False
-
-    def _compute_interaction_on_lag_grid_without_ghosting(self):
+    # ------------------------------------------------------------------ the two interactions
+    def _prepare(self):
+        """Fresh velocity ghost cells (points near a slab face interpolate across it) and current
+        Lagrangian kinematics."""
+        if self.auto_ghosting:
+            u = self.eul_grid_velocity_field
+            u.flags.writeable = True
+            self.mpi_ghost_exchange_communicator.exchange_vector_field_init(u)
+            self.mpi_ghost_exchange_communicator.exchange_finalise()
+            u.flags.writeable = False
         self.forcing_grid.compute_lag_grid_position_field()
         self.forcing_grid.compute_lag_grid_velocity_field()
+
+    def compute_interaction_on_lag_grid(self):
+        """Forces on the Lagrangian points only (the body's sub-steps between two flow steps)."""
+        self._prepare()
         self.compute_interaction_force_on_lag_grid(
             local_eul_grid_velocity_field=self.eul_grid_velocity_field,
             global_lag_grid_position_field=self.forcing_grid.position_field,
-            global_lag_grid_velocity_field=self.forcing_grid.velocity_field,
-        )
+            global_lag_grid_velocity_field=self.forcing_grid.velocity_field)
 
-    def _compute_interaction_on_lag_grid_with_ghosting(self):
-        self._ghost_velocity_field_for_interaction()
-        self._compute_interaction_on_lag_grid_without_ghosting()
-
-    def _compute_full_interaction_without_ghosting(self):
-        self.forcing_grid.compute_lag_grid_position_field()
-        self.forcing_grid.compute_lag_grid_velocity_field()
+    def compute_full_interaction(self):
+        """Forces on the Lagrangian points AND their reaction spread onto the Eulerian forcing field."""
+        self._prepare()
         self.compute_interaction_forcing(
             local_eul_grid_forcing_field=self.eul_grid_forcing_field,
             local_eul_grid_velocity_field=self.eul_grid_velocity_field,
             global_lag_grid_position_field=self.forcing_grid.position_field,
-            global_lag_grid_velocity_field=self.forcing_grid.velocity_field,
-        )
+            global_lag_grid_velocity_field=self.forcing_grid.velocity_field)
 
-    def _compute_full_interaction_with_ghosting(self):
-        self._ghost_velocity_field_for_interaction()
-        self._compute_full_interaction_without_ghosting()
+    __call__ = compute_full_interaction
 
     def compute_flow_forces_and_torques(self):
         self.compute_interaction_on_lag_grid()
         self.forcing_grid.transfer_forcing_from_grid_to_body(
-            body_flow_forces=self.body_flow_forces,
-            body_flow_torques=self.body_flow_torques,
-            lag_grid_forcing_field=self.global_lag_grid_forcing_field,
-        )
+            body_flow_forces=self.body_flow_forces, body_flow_torques=self.body_flow_torques,
+            lag_grid_forcing_field=self.global_lag_grid_forcing_field)
 
     def get_grid_deviation_error_l2_norm(self, compute_global=True):
+        """RMS distance between the forcing points and where the body wants them; the global value is
+        assembled on ``master_rank`` and handed to every rank."""
+        own = float(np.sum(np.square(self.local_lag_grid_position_mismatch_field)))
+        count = self.forcing_grid.num_lag_nodes
         if not compute_global:
-            return np.linalg.norm(self.local_lag_grid_position_mismatch_field) / np.sqrt(
-                self.forcing_grid.num_lag_nodes)
-        local_sq = np.linalg.norm(self.local_lag_grid_position_mismatch_field) ** 2
-        total = self.mpi_construct.grid.reduce(local_sq, op=MPI.SUM, root=self.master_rank)
-        if self.mpi_construct.rank == self.master_rank:
-            total = np.sqrt(total) / np.sqrt(self.forcing_grid.num_lag_nodes)
-        return self.mpi_construct.grid.bcast(total, root=self.master_rank)
+            return np.sqrt(own / count)
+        grid = self.mpi_construct.grid
+        total = grid.reduce(own, op=MPI.SUM, root=self.master_rank)
+        rms = np.sqrt(total / count) if self.mpi_construct.rank == self.master_rank else None
+        return grid.bcast(rms, root=self.master_rank)
 
 
 class _BodyFlowInteraction(ImmersedBodyFlowInteractionMPI):
