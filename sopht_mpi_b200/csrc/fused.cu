@@ -208,14 +208,41 @@ static int launch_fused(const SbGeom& g, void* out, const void* w, const void* u
   using FT = FusedTile<TY, TX, NT>;
   const size_t smem = sizeof(T) * FT::ELEMS;
   const unsigned gx = (g.mx + TX - 1) / TX, gy = (g.my + TY - 1) / TY;
-  // enough z chunks for several waves of 148 SMs x resident CTAs, each chunk at least 16 planes
-  int chunks = (int)((6 * 148 + gx * gy - 1) / (gx * gy));
-  if (chunks < 1) chunks = 1;
-  int zchunk = (g.mz + chunks - 1) / chunks;
-  if (zchunk < 16) zchunk = 16;
-  if (zchunk > g.mz) zchunk = g.mz;
-  chunks = (g.mz + zchunk - 1) / zchunk;
+  // z chunks: a block marches zchunk + 4 planes (4 to prime the rings), and the grid runs in waves of
+  // `resident` blocks; pick the chunk count that minimises waves x (zchunk + 4).  (6 chunks at 260^3
+  // were 918 blocks = 2.07 waves of 444: a third wave for 30 blocks.)
   SB_KERNEL_ATTR_SMEM((sb_vorticity_fused_kernel<T, TY, TX, NT>), smem);
+  long long resident = 148 * 3;
+#ifndef SB200_EMU
+  {
+    static long long cached = 0;
+    if (cached == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_vorticity_fused_kernel<T, TY, TX, NT>, NT, smem);
+      cached = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    }
+    resident = cached;
+  }
+#endif
+  int chunks = 1, zchunk = g.mz;
+  {
+    long long best = -1;
+    const long long tiles = (long long)gx * gy;
+    for (int c = 1; c <= g.mz; ++c) {
+      const int zc = (g.mz + c - 1) / c;
+      if (zc < 8 && c > 1) break;
+      const int cc = (g.mz + zc - 1) / zc;  // chunks actually needed for this chunk length
+      const long long waves = (tiles * cc + resident - 1) / resident;
+      const long long cost = waves * (zc + 4);
+      if (best < 0 || cost < best) {
+        best = cost;
+        chunks = cc;
+        zchunk = zc;
+      }
+    }
+  }
   SB_LAUNCH_COOP((sb_vorticity_fused_kernel<T, TY, TX, NT>), dim3(gx, gy, (unsigned)chunks), dim3(NT), smem,
                  stream, g, (T*)out, (const T*)w, (const T*)u, (T)p, (T)d, zchunk);
   SB_CHECK_LAUNCH("vorticity_fused");
