@@ -31,10 +31,24 @@ def default_device():
     return torch.device("cpu")
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_HAS_CUDA = None
+
+
 def current_stream_ptr(device=None):
-    if torch.cuda.is_available():
-        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    return ctypes.c_void_p(0)
+    """The current CUDA stream of `device` as a ``void*``.  Called once per kernel launch, so it takes
+    the raw-handle fast path (one C call) instead of building a ``torch.cuda.Stream`` object."""
+    global _HAS_CUDA
+    if _HAS_CUDA is None:
+        _HAS_CUDA = torch.cuda.is_available()
+    if not _HAS_CUDA:
+        return ctypes.c_void_p(0)
+    if _RAW_STREAM is not None:
+        index = getattr(device, "index", None) if device is not None else None
+        if index is None:
+            index = torch.cuda.current_device()
+        return ctypes.c_void_p(_RAW_STREAM(index))
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _unwrap(value):

@@ -17,6 +17,7 @@ from torch.multiprocessing.reductions import reduce_tensor
 
 from .. import _lib
 from .comm import host_group
+from .device import current_stream_ptr
 from .logger import logger
 
 
@@ -78,7 +79,7 @@ class PeerExchange:
             dist.all_to_all([empty if q == rank else d_blocks[q] for q in range(nranks)],
                             [empty if q == rank else s_blocks[q] for q in range(nranks)])
             return
-        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        stream = current_stream_ptr(self.device)
         plan = self._plans.get((dst, src))
         if plan is None:  # pointer tables of this (dst, src) pair, built once
             order = [(rank + k) % nranks for k in range(nranks)]  # local block first, then the ring

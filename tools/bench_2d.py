@@ -49,6 +49,17 @@ def main():
     ms = (time.perf_counter() - t0) / steps * 1e3
     print(f"2D cylinder 512x256 f64, 60 forcing points: {ms:.3f} ms per step, "
           f"{n[0] * n[1] / ms / 1e3:.1f} Mcell-updates/s, max vorticity {sim.get_max_vorticity():.3f}")
+    if "--profile" in sys.argv:
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(100):
+            one_step()
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr).sort_stats("tottime").print_stats(22)
 
 
 if __name__ == "__main__":
