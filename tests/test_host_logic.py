@@ -132,3 +132,21 @@ def test_two_rank_gloo_halo_fields_and_ownership():
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "DIST_WORKER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_row_block_magic_division_is_exact():
+    """`SbRowBlocks` (csrc/poisson_fft.cu) divides the bin index by the kx-block length with
+    umulhi(k, ceil(2^32 / kxl)) on the GPU (the emulation uses `/`): exact for every bin of every
+    supported row length and block length."""
+    k = np.arange(0, 4098, dtype=np.uint64)
+    for kxl in range(1, 4100):
+        magic = np.uint64((0x100000000 + kxl - 1) // kxl)
+        assert np.array_equal((k * magic) >> np.uint64(32), k // np.uint64(kxl)), kxl
+
+
+def test_slab_kx_block_length_rule():
+    """kx bins per rank: ceil((nx + 1) / P) rounded up to a multiple of 4, P blocks cover every bin."""
+    for nx in (16, 64, 256, 512, 1024, 4096):
+        for nranks in (2, 4, 8):
+            kxl = (((nx + 1 + nranks - 1) // nranks) + 3) & ~3
+            assert kxl % 4 == 0 and kxl * nranks >= nx + 1 and (kxl - 4) * nranks < nx + 1 + 3 * nranks
