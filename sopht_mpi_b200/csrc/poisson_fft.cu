@@ -621,7 +621,7 @@ template <typename T, typename Rows, bool PRUNED>
 static int launch_x_r2c(const SbFftPlan& plan, int ny, int nz, int ncomp, const Rows& rows, C2<T>* out,
                         long long pitch, const C2<T>* tw, const C2<T>* wpost, void* stream,
                         const SbRowBlocks& rb = SbRowBlocks()) {
-  if (sizeof(T) == 4 && PRUNED) {
+  if (PRUNED) {  // compile-time specialised lengths, float and double
     switch (plan.log2n) {
       case 8: return launch_x_r2c_c<T, Rows, PRUNED, 8>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream, rb);
       case 9: return launch_x_r2c_c<T, Rows, PRUNED, 9>(plan, ny, nz, ncomp, rows, out, pitch, tw, wpost, stream, rb);
@@ -650,7 +650,7 @@ template <typename T>
 static int launch_x_c2r(const SbFftPlan& plan, int ny, int nz, int ncomp, const C2<T>* in, long long pitch,
                         const FieldRows<T>& dst, const C2<T>* tw, const C2<T>* wpost, void* stream,
                         const SbRowBlocks& rb = SbRowBlocks()) {
-  if (sizeof(T) == 4) {
+  {
     switch (plan.log2n) {
       case 8: return launch_x_c2r_c<T, 8>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
       case 9: return launch_x_c2r_c<T, 9>(plan, ny, nz, ncomp, in, pitch, dst, tw, wpost, stream, rb);
@@ -749,12 +749,14 @@ static int launch_strided_c(const SbFftPlan& plan, const C2<T>* in, const SbLine
 template <typename T, int MODE>
 static int launch_strided(const SbFftPlan& plan, const C2<T>* in, const SbLines& lin, C2<T>* out,
                           const SbLines& lout, const C2<T>* tw, const SbGreensTable<T>& gt, void* stream) {
-  if (sizeof(T) == 4 && MODE != 3) {
+  if (MODE != 3) {  // compile-time specialised lengths (float: 256..2048, double: 256..1024)
     switch (plan.log2n) {
       case 8: return launch_strided_c<T, MODE, 8>(plan, in, lin, out, lout, tw, gt, stream);
       case 9: return launch_strided_c<T, MODE, 9>(plan, in, lin, out, lout, tw, gt, stream);
       case 10: return launch_strided_c<T, MODE, 10>(plan, in, lin, out, lout, tw, gt, stream);
-      case 11: return launch_strided_c<T, MODE, 11>(plan, in, lin, out, lout, tw, gt, stream);
+      case 11:
+        if (sizeof(T) == 4) return launch_strided_c<T, MODE, 11>(plan, in, lin, out, lout, tw, gt, stream);
+        break;
       default: break;
     }
   }
