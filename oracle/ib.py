@@ -106,6 +106,47 @@ def lagrangian_to_eulerian(eul_field, lag_field, weights, nearest, width):
             eul_field[win] += (lag_field[i] * weights[..., i]).astype(eul_field.dtype)
 
 
+def _window_indices(nearest, width):
+    """index arrays (array-axis order) of shape (N, 2w, .., 2w): point-major, so that a flattened
+    scatter visits the points in the reference's sequential order"""
+    dim, n = nearest.shape
+    off = np.arange(-width + 1, width + 1)
+    idx = []
+    for ax in range(dim):  # array axis ax <-> component dim - 1 - ax
+        shape = [1] * (dim + 1)
+        shape[1 + ax] = 2 * width
+        idx.append(nearest[dim - 1 - ax].reshape((n,) + (1,) * dim) + off.reshape(shape))
+    return tuple(np.broadcast_arrays(*idx))
+
+
+def eulerian_to_lagrangian_fast(lag_field, eul_field, weights, nearest, dx, width):
+    """Vectorised twin of :func:`eulerian_to_lagrangian` (gathers all windows at once) for the
+    timed CPU baseline; same products, numpy's pairwise summation instead of the loop's."""
+    dim = nearest.shape[0]
+    idx = _window_indices(nearest, width)
+    w = np.moveaxis(weights, -1, 0)  # (N, 2w, .., 2w)
+    axes = tuple(range(1, dim + 1))
+    if eul_field.ndim == dim + 1:
+        for c in range(eul_field.shape[0]):
+            lag_field[c] = np.sum(eul_field[c][idx] * w, axis=axes) * (dx ** dim)
+    else:
+        lag_field[...] = np.sum(eul_field[idx] * w, axis=axes) * (dx ** dim)
+
+
+def lagrangian_to_eulerian_fast(eul_field, lag_field, weights, nearest, width):
+    """Vectorised twin of :func:`lagrangian_to_eulerian`: ``np.add.at`` applies the updates in
+    index order, i.e. point after point like the reference loop."""
+    dim = nearest.shape[0]
+    idx = _window_indices(nearest, width)
+    w = np.moveaxis(weights, -1, 0)
+    bshape = (-1,) + (1,) * dim
+    if eul_field.ndim == dim + 1:
+        for c in range(eul_field.shape[0]):
+            np.add.at(eul_field[c], idx, (lag_field[c].reshape(bshape) * w).astype(eul_field.dtype))
+    else:
+        np.add.at(eul_field, idx, (lag_field.reshape(bshape) * w).astype(eul_field.dtype))
+
+
 def clear_ghost_cells_nd(field, gs, dim):
     """reference ...MPI3D.py:786-792 (last ``dim`` axes)."""
     for ax in range(-1, -dim - 1, -1):
@@ -141,8 +182,12 @@ class VirtualBoundaryForcingOracle:
     (all points local)."""
 
     def __init__(self, k, c, grid_dim, dx, real_t, lag_dtype, gs,
-                 eul_grid_coord_shift=None, width=2, kernel_type="cosine"):
+                 eul_grid_coord_shift=None, width=2, kernel_type="cosine", fast=False):
         self.k, self.c = k, c
+        # fast: vectorised gather / scatter (the reference's kernels are numba-compiled loops; a
+        # python-level loop over 1e5 points would misrepresent its speed in the CPU baseline)
+        self._e2l = eulerian_to_lagrangian_fast if fast else eulerian_to_lagrangian
+        self._l2e = lagrangian_to_eulerian_fast if fast else lagrangian_to_eulerian
         self.dim = grid_dim
         self.dx = dx
         self.real_t = real_t
@@ -172,16 +217,14 @@ class VirtualBoundaryForcingOracle:
             self.weights = cosine_weights(support, self.dx, self.real_t)
         else:
             self.weights = peskin_weights(support, self.dx, self.real_t)
-        eulerian_to_lagrangian(
-            self.flow_velocity, eul_velocity, self.weights, self.nearest, self.dx, self.width
-        )
+        self._e2l(self.flow_velocity, eul_velocity, self.weights, self.nearest, self.dx, self.width)
         self.velocity_mismatch[...] = self.flow_velocity - lag_vel
         self.forcing[...] = self.k * self.position_mismatch + self.c * self.velocity_mismatch
 
     def compute_interaction_force_on_eul_and_lag_grid(self, eul_forcing, eul_velocity,
                                                       lag_pos, lag_vel):
         self.compute_interaction_force_on_lag_grid(eul_velocity, lag_pos, lag_vel)
-        lagrangian_to_eulerian(eul_forcing, self.forcing, self.weights, self.nearest, self.width)
+        self._l2e(eul_forcing, self.forcing, self.weights, self.nearest, self.width)
         # single rank: every neighbour is PROC_NULL -> ghost sum only clears ghosts
         clear_ghost_cells_nd(eul_forcing, self.gs, self.dim)
 

@@ -10,20 +10,35 @@ from ...utils.comm import MPI
 from .immersed_body_forcing_grid import EmptyForcingGrid
 
 
-def _report_lagrangian_resolution(grid_name, max_lag_grid_dx, dx):
-    """One log record telling the user how the forcing-point spacing compares with the flow grid
-    (the coupling works best for spacings between dx / 2 and 2 dx)."""
-    ratio = max_lag_grid_dx / dx
-    if ratio > 2.0:
-        verdict = ("too coarse for the flow grid (more than 2 dx between forcing points): the body leaks, "
-                   "refine the Lagrangian grid")
-    elif ratio < 0.5:
-        verdict = ("finer than the flow grid needs (less than dx / 2 between forcing points): redundant "
-                   "points, coarsen the Lagrangian grid")
+_RULE = "=========================================================="
+
+
+def _warn_about_lagrangian_resolution(grid_type, max_lag_grid_dx, dx):
+    """The three resolution messages of the reference, word for word (its tests match on them,
+    ``tests/test_simulator/immersed_body/test_immersed_body_interaction_mpi.py:57-94``;
+    reference ``immersed_body_flow_interaction_mpi.py:49-79``): the delta function spans two
+    flow cells, so a spacing above 2 dx leaks and one below dx / 2 is redundant."""
+    logger.warning(f"{_RULE}\nFor {grid_type}:")
+    if max_lag_grid_dx > 2 * dx:
+        logger.warning(
+            f"Eulerian grid spacing (dx): {dx}"
+            f"\nMax Lagrangian grid spacing: {max_lag_grid_dx} > 2 * dx"
+            "\nThe Lagrangian grid of the body is too coarse relative to"
+            "\nthe Eulerian grid of the flow, which can lead to unexpected"
+            "\nconvergence. Please make the Lagrangian grid finer.")
+    elif max_lag_grid_dx < 0.5 * dx:
+        logger.warning(
+            f"{_RULE}\n"
+            f"Eulerian grid spacing (dx): {dx}"
+            f"\nMax Lagrangian grid spacing: {max_lag_grid_dx} < 0.5 * dx"
+            "\nThe Lagrangian grid of the body is too fine relative to"
+            "\nthe Eulerian grid of the flow, which corresponds to redundant"
+            "\nforcing points. Please make the Lagrangian grid coarser.")
     else:
-        verdict = "matched to the flow grid"
-    logger.warning(f"{grid_name}: max Lagrangian spacing {max_lag_grid_dx:.6g} = {ratio:.3g} dx "
-                   f"(dx = {dx:.6g}) is {verdict}")
+        logger.warning(
+            "Lagrangian grid is resolved almost the same as the Eulerian"
+            "\ngrid of the flow.")
+    logger.warning(_RULE)
 
 
 class ImmersedBodyFlowInteractionMPI(VirtualBoundaryForcingMPI):
@@ -39,16 +54,15 @@ class ImmersedBodyFlowInteractionMPI(VirtualBoundaryForcingMPI):
                  enable_eul_grid_forcing_reset=False, start_time=0.0, assume_data_locality=False,
                  auto_ghosting=True):
         self.mpi_ghost_exchange_communicator = mpi_ghost_exchange_communicator
-        self.auto_ghosting = bool(auto_ghosting)
         # views: the interactor follows whatever the simulator does to its fields
         self.eul_grid_forcing_field = eul_grid_forcing_field.view()
         self.eul_grid_velocity_field = eul_grid_velocity_field.view()
         self.eul_grid_velocity_field.flags.writeable = False
 
-        spacing = mpi_construct.grid.bcast(self.forcing_grid.get_maximum_lagrangian_grid_spacing(),
-                                           root=self.master_rank)
-        _report_lagrangian_resolution(type(self.forcing_grid).__name__, spacing, dx)
-        area = spacing ** (grid_dim - 1)
+        max_lag_grid_dx = mpi_construct.grid.bcast(
+            self.forcing_grid.get_maximum_lagrangian_grid_spacing(), root=self.master_rank)
+        _warn_about_lagrangian_resolution(type(self.forcing_grid).__name__, max_lag_grid_dx, dx)
+        area = max_lag_grid_dx ** (grid_dim - 1)
         VirtualBoundaryForcingMPI.__init__(
             self, mpi_construct=mpi_construct, ghost_size=mpi_ghost_exchange_communicator.ghost_size,
             virtual_boundary_stiffness_coeff=virtual_boundary_stiffness_coeff * area,
@@ -57,41 +71,60 @@ class ImmersedBodyFlowInteractionMPI(VirtualBoundaryForcingMPI):
             enable_eul_grid_forcing_reset=enable_eul_grid_forcing_reset, start_time=start_time,
             master_rank=self.master_rank, global_lag_grid_position_field=self.forcing_grid.position_field,
             assume_data_locality=assume_data_locality)
-        if not self.auto_ghosting:
-            logger.warning("interactor created with auto_ghosting=False: exchange the velocity ghost cells "
-                           "yourself before every interaction")
+        # the public entry points are bound per instance, as in the reference (:104-121), so user
+        # code may swap them
+        if auto_ghosting:
+            self.compute_full_interaction = self._compute_full_interaction_with_ghosting
+            self.compute_interaction_on_lag_grid = self._compute_interaction_on_lag_grid_with_ghosting
+        else:
+            logger.warning(
+                f"{_RULE}\n"
+                "Auto ghosting of velocity field is disabled for interactor.\n"
+                "Please ensure ghosting is done before calling interactor functions.\n"
+                f"{_RULE}")
+            self.compute_full_interaction = self._compute_full_interaction_without_ghosting
+            self.compute_interaction_on_lag_grid = self._compute_interaction_on_lag_grid_without_ghosting
+
+    def __call__(self):
+        self.compute_full_interaction()
 
     # ------------------------------------------------------------------ the two interactions
-    def _prepare(self):
-        """Fresh velocity ghost cells (points near a slab face interpolate across it) and current
-        Lagrangian kinematics."""
-        if self.auto_ghosting:
-            u = self.eul_grid_velocity_field
-            u.flags.writeable = True
-            self.mpi_ghost_exchange_communicator.exchange_vector_field_init(u)
-            self.mpi_ghost_exchange_communicator.exchange_finalise()
-            u.flags.writeable = False
+    def _ghost_velocity_field_for_interaction(self):
+        """Fresh velocity ghost cells: points near a slab face interpolate across it."""
+        u = self.eul_grid_velocity_field
+        u.flags.writeable = True
+        self.mpi_ghost_exchange_communicator.exchange_vector_field_init(u)
+        self.mpi_ghost_exchange_communicator.exchange_finalise()
+        u.flags.writeable = False
+
+    def _update_lagrangian_kinematics(self):
         self.forcing_grid.compute_lag_grid_position_field()
         self.forcing_grid.compute_lag_grid_velocity_field()
 
-    def compute_interaction_on_lag_grid(self):
+    def _compute_interaction_on_lag_grid_without_ghosting(self):
         """Forces on the Lagrangian points only (the body's sub-steps between two flow steps)."""
-        self._prepare()
+        self._update_lagrangian_kinematics()
         self.compute_interaction_force_on_lag_grid(
             local_eul_grid_velocity_field=self.eul_grid_velocity_field,
             global_lag_grid_position_field=self.forcing_grid.position_field,
             global_lag_grid_velocity_field=self.forcing_grid.velocity_field)
 
-    def compute_full_interaction(self):
+    def _compute_interaction_on_lag_grid_with_ghosting(self):
+        self._ghost_velocity_field_for_interaction()
+        self._compute_interaction_on_lag_grid_without_ghosting()
+
+    def _compute_full_interaction_without_ghosting(self):
         """Forces on the Lagrangian points AND their reaction spread onto the Eulerian forcing field."""
-        self._prepare()
+        self._update_lagrangian_kinematics()
         self.compute_interaction_forcing(
             local_eul_grid_forcing_field=self.eul_grid_forcing_field,
             local_eul_grid_velocity_field=self.eul_grid_velocity_field,
             global_lag_grid_position_field=self.forcing_grid.position_field,
             global_lag_grid_velocity_field=self.forcing_grid.velocity_field)
 
-    __call__ = compute_full_interaction
+    def _compute_full_interaction_with_ghosting(self):
+        self._ghost_velocity_field_for_interaction()
+        self._compute_full_interaction_without_ghosting()
 
     def compute_flow_forces_and_torques(self):
         self.compute_interaction_on_lag_grid()

@@ -1,5 +1,9 @@
 """Print the metrics that matter from an .ncu-rep (raw page csv) for every profiled launch."""
+import argparse
 import csv
+import json
+import os
+import re
 import subprocess
 import sys
 
@@ -28,18 +32,55 @@ WANT = [
 ]
 
 
-def main(path):
+def _num(text):
+    try:
+        return float(text.replace(",", ""))
+    except ValueError:
+        return 0.0
+
+
+def _bytes(value, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return _num(value) * scale.get(unit, 1.0)
+
+
+def main(path, traffic_json=None, workload=None, kernel_regex=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
+    best = None
     for r in rows[2:]:
         print("==== ", r[ki][:100])
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
                 print(f"  {w:82s} {r[i]:>16s} {units[i]}")
+        if traffic_json and re.search(kernel_regex, r[ki]):
+            ir, iw, it = (hdr.index(k) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum",
+                                                   "gpu__time_duration.sum"))
+            rec = {"kernel": r[ki][:160], "dram_bytes_read": _bytes(r[ir], units[ir]),
+                   "dram_bytes_write": _bytes(r[iw], units[iw]), "duration": _num(r[it]), "duration_unit": units[it],
+                   "source": os.path.basename(path)}
+            rec["dram_bytes_per_launch"] = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+            if best is None or rec["duration"] > best["duration"]:
+                best = rec
+    if traffic_json and best:
+        # bench.py reads roofline.traffic from this file: DRAM bytes of one launch of the dominant kernel
+        try:
+            table = json.load(open(traffic_json))
+        except (OSError, ValueError):
+            table = {}
+        table[workload] = best
+        json.dump(table, open(traffic_json, "w"), indent=1, sort_keys=True)
+        print(f"traffic of {workload}: {best['dram_bytes_per_launch']:.4g} bytes per launch -> {traffic_json}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    ap = argparse.ArgumentParser()
+    ap.add_argument("report")
+    ap.add_argument("--traffic-json", default=None)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--kernel-regex", default=r"sb_fft_strided(32)?_kernel<.*?, *\(?int\)?1,")
+    a = ap.parse_args()
+    main(a.report, a.traffic_json, a.workload, a.kernel_regex)
