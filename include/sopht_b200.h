@@ -201,6 +201,28 @@ int sb200_ib_interact_lag(const sb200_grid_t* g, const sb200_ib_params_t* p, int
 /* L->E spreading without ghost sum: ...MPI3D.py:329-427 */
 int sb200_ib_spread(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n, void* eul_forcing,
                     const void* lag_forcing, const void* lag_position, void* stream);
+/* Lagrangian rank ownership on the device: utils/mpi_utils_3d.py:1352-1384 (`_compute_lag_nodes_rank_address`),
+ * mpi_utils_2d.py:611-637.  rank_address[i] (int32, device) = row-major Cartesian rank of the block
+ * coordinates ((pos - shift) / sub_dx).astype(int32) of point i; sub_dx_zyx = eul_grid_dx * local grid
+ * size per ARRAY axis (z,y,x; 2D: entry 0 unused), topo_zyx the grid topology in the same order (host
+ * arrays of 3).  *out_of_domain_flag (device int32, may be NULL) is set to 1 if a block coordinate falls
+ * outside the topology (the reference logs an error and aborts). */
+int sb200_ib_rank_address(int lag_dtype, int dim, int64_t n, const void* lag_position, double coord_shift,
+                          const double* sub_dx_zyx, const int32_t* topo_zyx, void* rank_address,
+                          void* out_of_domain_flag, void* stream);
+/* sb200_ib_interact_lag / sb200_ib_spread over GLOBAL (replicated) Lagrangian arrays, restricted to the
+ * points with rank_address[i] == my_rank (rank_address NULL: all points); the interaction writes zeros
+ * for the other points so that one SUM all-reduce assembles the global arrays: replaces
+ * MPILagrangianFieldCommunicator3D.scatter_global_field / gather_local_field
+ * (utils/mpi_utils_3d.py:1410-1459) and VirtualBoundaryForcingMPI.update_buffers (:238-276). */
+int sb200_ib_interact_owned(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n,
+                            const void* eul_velocity, const void* lag_position, const void* lag_velocity,
+                            const void* position_mismatch, void* nearest, void* weights, void* flow_velocity,
+                            void* velocity_mismatch, void* forcing, const void* rank_address, int my_rank,
+                            void* stream);
+int sb200_ib_spread_owned(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n, void* eul_forcing,
+                          const void* lag_forcing, const void* lag_position, const void* rank_address,
+                          int my_rank, void* stream);
 /* zero all ghost cells: ...MPI3D.py:786-792 */
 int sb200_clear_ghost_cells(const sb200_grid_t* g, void* field, int ncomp, void* stream);
 /* dst interior-adjacent layers += src slab (ghost-sum receive side): ...MPI3D.py:689-784 */

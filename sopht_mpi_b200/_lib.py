@@ -89,6 +89,10 @@ PROTOTYPES = {
     "sb200_poisson_slab_backward": (c_int, [_V, _V, c_int, _V, _V]),
     "sb200_ib_interact_lag": (c_int, [_G, _P, c_int64, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sb200_ib_spread": (c_int, [_G, _P, c_int64, _V, _V, _V, _V]),
+    "sb200_ib_rank_address": (c_int, [c_int, c_int, c_int64, _V, c_double, POINTER(c_double), POINTER(c_int32), _V,
+                                      _V, _V]),
+    "sb200_ib_interact_owned": (c_int, [_G, _P, c_int64, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, c_int, _V]),
+    "sb200_ib_spread_owned": (c_int, [_G, _P, c_int64, _V, _V, _V, _V, c_int, _V]),
     "sb200_clear_ghost_cells": (c_int, [_G, _V, c_int, _V]),
     "sb200_ghost_sum_add_z": (c_int, [_G, _V, c_int, _V, _V, _V]),
     "sb200_ib_interpolate": (c_int, [_G, _P, c_int64, c_int, _V, _V, _V, _V]),

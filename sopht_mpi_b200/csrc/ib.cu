@@ -67,10 +67,20 @@ template <typename TE, typename TL, typename TC>
 __global__ void __launch_bounds__(128)
     sb_ib_interact_kernel(SbGeom g, SbIbP<TL> P, long long n, int ncomp, const TE* eul, const TL* pos,
                           const TL* vel, const TL* dpos, long long* nearest_out, TL* weights_out,
-                          TL* flow_vel, TL* dvel, TL* force, double dx_pow_dim, TL kcoef, TL ccoef) {
+                          TL* flow_vel, TL* dvel, TL* force, double dx_pow_dim, TL kcoef, TL ccoef,
+                          const int* __restrict__ owner, int my_rank) {
   const unsigned lane = threadIdx.x & 31;
   const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pt >= n) return;  // whole warp exits together
+  if (owner && owner[pt] != my_rank) {
+    // another rank's point: zeros, so that a SUM all-reduce over the ranks assembles the global arrays
+    if (lane == 0)
+      for (int c = 0; c < ncomp; ++c) {
+        flow_vel[c * n + pt] = TL(0);
+        if (force) dvel[c * n + pt] = force[c * n + pt] = TL(0);
+      }
+    return;
+  }
   const int dim = P.dim, kw = 2 * P.width;
   long long near[3] = {0, 0, 0};
   TL p[3] = {0, 0, 0};
@@ -88,6 +98,9 @@ __global__ void __launch_bounds__(128)
     TL w = P.weight_prefac * sb_delta_1d(P, sb_support_scaled(P, near[0], kx + off0, p[0], 0));
     w = w * sb_delta_1d(P, sb_support_scaled(P, near[1], ky + off0, p[1], 1));
     if (dim == 3) w = w * sb_delta_1d(P, sb_support_scaled(P, near[2], kz + off0, p[2], 2));
+    // the reference's Peskin kernel hands back weights rounded to real_t even when the Lagrangian
+    // arrays are wider (tests/golden/ib_*_f32_f64.npz: every w_pes value is a float32 number)
+    if (P.kernel_type == 1) w = (TL)(TE)w;
     if (weights_out) weights_out[(long long)cell * n + pt] = w;
     const long long x = near[0] + kx + off0, y = near[1] + ky + off0;
     const long long z = dim == 3 ? near[2] + kz + off0 : 0;
@@ -113,10 +126,12 @@ __global__ void __launch_bounds__(128)
 
 template <typename TE, typename TL, typename TC>
 __global__ void __launch_bounds__(128)
-    sb_ib_spread_kernel(SbGeom g, SbIbP<TL> P, long long n, TE* eul, const TL* lag, const TL* pos) {
+    sb_ib_spread_kernel(SbGeom g, SbIbP<TL> P, long long n, TE* eul, const TL* lag, const TL* pos,
+                        const int* __restrict__ owner, int my_rank) {
   const unsigned lane = threadIdx.x & 31;
   const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pt >= n) return;
+  if (owner && owner[pt] != my_rank) return;
   const int dim = P.dim, kw = 2 * P.width;
   long long near[3] = {0, 0, 0};
   TL p[3] = {0, 0, 0}, f[3] = {0, 0, 0};
@@ -132,6 +147,9 @@ __global__ void __launch_bounds__(128)
     TL w = P.weight_prefac * sb_delta_1d(P, sb_support_scaled(P, near[0], kx + off0, p[0], 0));
     w = w * sb_delta_1d(P, sb_support_scaled(P, near[1], ky + off0, p[1], 1));
     if (dim == 3) w = w * sb_delta_1d(P, sb_support_scaled(P, near[2], kz + off0, p[2], 2));
+    // the reference's Peskin kernel hands back weights rounded to real_t even when the Lagrangian
+    // arrays are wider (tests/golden/ib_*_f32_f64.npz: every w_pes value is a float32 number)
+    if (P.kernel_type == 1) w = (TL)(TE)w;
     const long long x = near[0] + kx + off0, y = near[1] + ky + off0;
     const long long z = dim == 3 ? near[2] + kz + off0 : 0;
     if (x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz) {
@@ -168,7 +186,7 @@ template <typename TE, typename TL>
 static int ib_interact_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, long long n, int ncomp,
                          const void* eul, const void* pos, const void* vel, const void* dpos,
                          void* nearest, void* weights, void* flow_vel, void* dvel, void* force,
-                         void* stream) {
+                         void* stream, const int* owner = nullptr, int my_rank = 0) {
   // index arithmetic in the promoted type of (lag dtype, real_t)
   using TC = typename std::conditional<(sizeof(TE) > sizeof(TL)), TE, TL>::type;
   SbGeom g;
@@ -190,14 +208,15 @@ static int ib_interact_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, lon
   SB_LAUNCH_COOP((sb_ib_interact_kernel<TE, TL, TC>), grid, block, 0, stream, g, P, n, ncomp,
                  (const TE*)eul, (const TL*)pos, (const TL*)vel, (const TL*)dpos, (long long*)nearest,
                  (TL*)weights, (TL*)flow_vel, (TL*)dvel, (TL*)force, dxp, (TL)p->stiffness,
-                 (TL)p->damping);
+                 (TL)p->damping, owner, my_rank);
   SB_CHECK_LAUNCH("ib_interact");
   return 0;
 }
 
 template <typename TE, typename TL>
 static int ib_spread_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, long long n, void* eul,
-                       const void* lag, const void* pos, void* stream) {
+                       const void* lag, const void* pos, void* stream, const int* owner = nullptr,
+                       int my_rank = 0) {
   using TC = typename std::conditional<(sizeof(TE) > sizeof(TL)), TE, TL>::type;
   SbGeom g;
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
@@ -207,7 +226,7 @@ static int ib_spread_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, long 
   const int warps = 4;
   dim3 block(32 * warps), grid((unsigned)((n + warps - 1) / warps));
   SB_LAUNCH_COOP((sb_ib_spread_kernel<TE, TL, TC>), grid, block, 0, stream, g, P, n, (TE*)eul,
-                 (const TL*)lag, (const TL*)pos);
+                 (const TL*)lag, (const TL*)pos, owner, my_rank);
   SB_CHECK_LAUNCH("ib_spread");
   return 0;
 }
@@ -260,6 +279,96 @@ extern "C" int sb200_ib_spread(const sb200_grid_t* g, const sb200_ib_params_t* p
   SB_REQUIRE(p->width == 2, "Interpolation kernel inconsistent with interpolation kernel width!");
   SB_DISPATCH_2(g->dtype, p->lag_dtype,
                 return (ib_spread_t<TE, TL>(g, p, n, eul_forcing, lag_forcing, lag_position, stream)));
+}
+
+// ---------------------------------------------- Lagrangian rank ownership (L1) on the device
+// rank_address[i] = rank_map[cz, cy, cx] with the block coordinate of every array axis
+//   ((pos - shift) / (dx * n_local_axis)).astype(int32)      (truncation toward zero)
+// evaluated like numpy evaluates the reference expression (utils/mpi_utils_3d.py:1357-1384,
+// mpi_utils_2d.py:611-637): the subtraction in the dtype of the positions, the division in double
+// (`eul_subblock_dx` is a float64 array).  `flag` (device int, may be NULL) is set to 1 when a point
+// lies beyond the topology (the reference aborts; the caller raises).
+template <typename TL>
+struct RankAddressOp {
+  const TL* pos;
+  int* out;
+  int* flag;
+  long long n;
+  int dim;
+  int topo[3];      // array order (z,y,x); 2D: topo[0] = 1
+  double sub_dx[3];
+  TL shift;
+  SB_D void operator()(long long i) const {
+    int rank = 0;
+    bool bad = false;
+    for (int ax = 3 - dim; ax < 3; ++ax) {
+      const TL d = pos[(long long)(2 - ax) * n + i] - shift;  // positions are x,y,z: component 2 - ax
+      int c = (int)((double)d / sub_dx[ax]);
+      if (c >= topo[ax]) bad = true;
+      if (c < 0) c += topo[ax];  // numpy's negative-index wrap of rank_map[...]
+      if (c < 0 || c >= topo[ax]) {
+        bad = true;
+        c = 0;
+      }
+      rank = rank * topo[ax] + c;
+    }
+    out[i] = rank;
+    if (bad && flag) *flag = 1;
+  }
+};
+
+template <typename T>
+static int ib_rank_address_t(int dim, long long n, const void* pos, double shift, const double* sub_dx,
+                             const int32_t* topo, void* out, void* flag, void* stream) {
+  RankAddressOp<T> op;
+  op.pos = (const T*)pos;
+  op.out = (int*)out;
+  op.flag = (int*)flag;
+  op.n = n;
+  op.dim = dim;
+  for (int a = 0; a < 3; ++a) {
+    op.topo[a] = topo[a];
+    op.sub_dx[a] = sub_dx[a];
+  }
+  op.shift = (T)shift;
+  return sb_launch_flat(n, op, stream, "ib_rank_address");
+}
+extern "C" int sb200_ib_rank_address(int lag_dtype, int dim, int64_t n, const void* lag_position,
+                                     double coord_shift, const double* sub_dx_zyx, const int32_t* topo_zyx,
+                                     void* rank_address, void* out_of_domain_flag, void* stream) {
+  SB_REQUIRE(dim == 2 || dim == 3, "ib_rank_address: dim must be 2 or 3");
+  SB_REQUIRE(lag_position && rank_address && sub_dx_zyx && topo_zyx, "ib_rank_address: null pointer");
+  if (n <= 0) return 0;
+  SB_DISPATCH_DTYPE(lag_dtype, return ib_rank_address_t<T>(dim, n, lag_position, coord_shift, sub_dx_zyx, topo_zyx,
+                                                           rank_address, out_of_domain_flag, stream));
+}
+
+// the same kernels restricted to the points this rank owns (`rank_address[i] == my_rank`); the
+// interaction writes zeros for the others (VirtualBoundaryForcingMPI keeps replicated global arrays
+// and assembles them with one SUM all-reduce instead of the reference's master scatter / gather,
+// utils/mpi_utils_3d.py:1386-1459)
+extern "C" int sb200_ib_interact_owned(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n,
+                                       const void* eul_velocity, const void* lag_position,
+                                       const void* lag_velocity, const void* position_mismatch, void* nearest,
+                                       void* weights, void* flow_velocity, void* velocity_mismatch,
+                                       void* forcing, const void* rank_address, int my_rank, void* stream) {
+  SB_REQUIRE(g && p, "ib: null params");
+  SB_REQUIRE(p->width == 2, "Interpolation kernel inconsistent with interpolation kernel width!");
+  SB_REQUIRE(g->gs >= p->width, "ghost size needs to be >= interp kernel width");
+  SB_DISPATCH_2(g->dtype, p->lag_dtype,
+                return (ib_interact_t<TE, TL>(g, p, n, g->dim, eul_velocity, lag_position, lag_velocity,
+                                              position_mismatch, nearest, weights, flow_velocity,
+                                              velocity_mismatch, forcing, stream, (const int*)rank_address,
+                                              my_rank)));
+}
+extern "C" int sb200_ib_spread_owned(const sb200_grid_t* g, const sb200_ib_params_t* p, int64_t n,
+                                     void* eul_forcing, const void* lag_forcing, const void* lag_position,
+                                     const void* rank_address, int my_rank, void* stream) {
+  SB_REQUIRE(g && p, "ib: null params");
+  SB_REQUIRE(p->width == 2, "Interpolation kernel inconsistent with interpolation kernel width!");
+  SB_DISPATCH_2(g->dtype, p->lag_dtype,
+                return (ib_spread_t<TE, TL>(g, p, n, eul_forcing, lag_forcing, lag_position, stream,
+                                            (const int*)rank_address, my_rank)));
 }
 
 // ------------------------------------------------------------ ghost cells --

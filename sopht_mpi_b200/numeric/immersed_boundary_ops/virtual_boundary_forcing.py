@@ -1,18 +1,36 @@
-"""Virtual boundary forcing (penalty immersed-boundary coupling).
+"""Virtual boundary forcing (penalty immersed-boundary coupling), device resident.
 
-Mirror of ``sopht_mpi/numeric/immersed_boundary_ops/VirtualBoundaryForcingMPI.py:21-459``:
-same constructor, same public buffers (host numpy arrays with the reference's names,
-which tests and the restart example read AND assign), same method names.  The
-Lagrangian work runs on the device: positions / body velocities / position mismatch
-are uploaded, one fused kernel does nearest index + weights + E->L interpolation +
-mismatch + penalty force, one kernel spreads the force (L->E), and the small
-``(dim, n)`` results are mirrored back to the host buffers.
+Mirror of ``sopht_mpi/numeric/immersed_boundary_ops/VirtualBoundaryForcingMPI.py:21-459``: same
+constructor, same method names, same public buffers (host numpy arrays with the reference's names,
+which tests and the restart example read AND assign).
+
+How the Lagrangian state is kept (B200 design):
+
+* every rank holds the GLOBAL ``(dim, N)`` Lagrangian arrays on its GPU (N ~ 1e4-1e5 points: a few MB);
+  the master rank uploads the body's positions / velocities once per interaction and broadcasts them
+  over NCCL, every rank computes the rank ownership of all points itself
+  (``sb200_ib_rank_address``: the reference expression, identical integers) and runs the fused
+  interaction / spreading kernels on the points it owns; one SUM all-reduce of (flow velocity,
+  velocity mismatch, force) assembles the global arrays.  This replaces the reference's hub-and-spoke
+  scatter / gather through the master and ``update_buffers`` (migration of the mismatch state is
+  implicit: the position mismatch is integrated for ALL points on EVERY rank from the all-reduced
+  velocity mismatch, so it is always globally consistent);
+* nothing is read back per interaction.  The host attributes (``global_lag_grid_forcing_field``,
+  ``local_lag_grid_position_mismatch_field`` ...) are lazy pinned mirrors: reading one downloads it
+  if the device copy is newer; an array that was handed out is treated as possibly modified and is
+  uploaded before the next kernel that consumes it; while somebody keeps a reference to it, it is
+  refreshed after every device update (reference semantics for IO objects that hold the arrays).
 """
+import ctypes
+import sys
+
 import numpy as np
 import torch
+import torch.distributed as dist
 
-from ...utils.comm import MPI
-from ...utils.device import Staged, torch_dtype
+from ... import _lib
+from ...utils import logger
+from ...utils.device import Staged, current_stream_ptr, dptr, torch_dtype
 from ...utils.mpi_utils_2d import MPILagrangianFieldCommunicator2D
 from ...utils.mpi_utils_3d import MPILagrangianFieldCommunicator3D
 from ..eulerian_grid_ops.ops import gen_set_fixed_val_pyst_kernel_2d, gen_set_fixed_val_pyst_kernel_3d
@@ -20,6 +38,56 @@ from .eulerian_lagrangian_grid_communicator import (
     EulerianLagrangianGridCommunicatorMPI2D,
     EulerianLagrangianGridCommunicatorMPI3D,
 )
+
+
+class _Mirror:
+    """Pinned host mirror of one device array with lazy coherence (see the module docstring)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.pinned = torch.zeros(tuple(dev.shape), dtype=dev.dtype, pin_memory=dev.is_cuda)
+        self.host = self.pinned.numpy()
+        self.device_newer = False
+        self.host_dirty = False
+        self._own_refs = sys.getrefcount(self.host)
+
+    def _held_outside(self):
+        return sys.getrefcount(self.host) > self._own_refs
+
+    def _download(self):
+        self.pinned.copy_(self.dev, non_blocking=True)
+        if self.dev.is_cuda:
+            torch.cuda.current_stream(self.dev.device).synchronize()
+        self.device_newer = False
+
+    def read(self):
+        """the host array, current; the caller may write into it"""
+        if self.device_newer:
+            self._download()
+        self.host_dirty = True
+        return self.host
+
+    def peek(self):
+        """the host array, current, for internal read-only use"""
+        if self.device_newer:
+            self._download()
+        return self.host
+
+    def before_device_read(self):
+        if self.host_dirty or self._held_outside():
+            if self.device_newer:  # (never handed out since the device wrote it: nothing to upload)
+                return
+            self.dev.copy_(self.pinned, non_blocking=True)
+            if self.dev.is_cuda and self._held_outside():
+                # the holder may write again at any time: the DMA must have read the buffer first
+                torch.cuda.current_stream(self.dev.device).synchronize()
+            self.host_dirty = False
+
+    def after_device_write(self):
+        self.host_dirty = False
+        self.device_newer = True
+        if self._held_outside():
+            self._download()
 
 
 class VirtualBoundaryForcingMPI:
@@ -59,12 +127,16 @@ class VirtualBoundaryForcingMPI:
                 f"Field ghost size {ghost_size} needs to be larger than "
                 f"interpolation kernel width {self.interp_kernel_width}")
         self.mpi_construct = mpi_construct
+        self.master_rank = master_rank
         self.device = mpi_construct.device
+        self.lib = _lib.load()
         lag_comm_cls = (MPILagrangianFieldCommunicator2D if grid_dim == 2
                         else MPILagrangianFieldCommunicator3D)
         comm_cls = (EulerianLagrangianGridCommunicatorMPI2D if grid_dim == 2
                     else EulerianLagrangianGridCommunicatorMPI3D)
+        self._replicated = (not assume_data_locality) and mpi_construct.size > 1
         if not self.assume_data_locality:
+            # host-side twin of the ownership map (reference API: tests and the restart recipe call it)
             self.mpi_lagrangian_field_communicator = lag_comm_cls(
                 eul_grid_dx=dx,
                 eul_grid_coord_shift=eul_grid_coord_shift,
@@ -72,6 +144,15 @@ class VirtualBoundaryForcingMPI:
                 master_rank=master_rank,
                 real_t=self.lag_grid_real_t,
             )
+            self.mpi_lagrangian_field_communicator.map_lagrangian_nodes_based_on_position(
+                global_lag_positions=global_lag_grid_position_field)
+            self.global_num_lag_nodes = int(self.mpi_lagrangian_field_communicator.rank_address.shape[-1])
+            sub_dx = np.asarray(self.mpi_lagrangian_field_communicator.eul_subblock_dx, dtype=np.float64)
+            pad = 3 - grid_dim
+            self._sub_dx = (ctypes.c_double * 3)(*([1.0] * pad + [float(v) for v in sub_dx]))
+            self._topo = (ctypes.c_int32 * 3)(*([1] * pad + [int(v) for v in mpi_construct.grid_topology]))
+        else:
+            self.global_num_lag_nodes = int(global_lag_grid_position_field.shape[-1])
         self.eul_lag_grid_communicator = comm_cls(
             dx=dx,
             eul_grid_coord_shift=eul_grid_coord_shift,
@@ -81,17 +162,9 @@ class VirtualBoundaryForcingMPI:
             mpi_construct=mpi_construct,
             ghost_size=ghost_size,
         )
-        if not self.assume_data_locality:
-            self.mpi_lagrangian_field_communicator.map_lagrangian_nodes_based_on_position(
-                global_lag_positions=global_lag_grid_position_field)
-            self.local_num_lag_nodes = self.mpi_lagrangian_field_communicator.local_num_lag_nodes
-            self.global_num_lag_nodes = self.mpi_lagrangian_field_communicator.rank_address.shape[-1]
-        else:
-            self.local_num_lag_nodes = global_lag_grid_position_field.shape[-1]
-            self.global_num_lag_nodes = self.local_num_lag_nodes
-
-        self._init_local_buffers(self.local_num_lag_nodes)
-        self._init_global_buffers()
+        self._coord_shift = float(eul_grid_coord_shift)
+        self._fetch_index_and_weights = False
+        self._init_local_buffers(None)
 
         if enable_eul_grid_forcing_reset:
             gen = gen_set_fixed_val_pyst_kernel_2d if grid_dim == 2 else gen_set_fixed_val_pyst_kernel_3d
@@ -102,67 +175,140 @@ class VirtualBoundaryForcingMPI:
             self.compute_interaction_forcing = self.compute_interaction_force_on_eul_and_lag_grid
 
     # ------------------------------------------------------------------ buffers
-    def _init_global_buffers(self):
-        if not self.assume_data_locality:
-            self.global_lag_grid_position_mismatch_field = np.zeros(
-                (self.grid_dim, self.global_num_lag_nodes), dtype=self.lag_grid_real_t)
-            self.global_lag_grid_velocity_mismatch_field = np.zeros_like(
-                self.global_lag_grid_position_mismatch_field)
-            self.global_lag_grid_forcing_field = np.zeros_like(
-                self.global_lag_grid_position_mismatch_field)
-        else:
-            self.global_lag_grid_position_mismatch_field = (
-                self.local_lag_grid_position_mismatch_field.view())
-            self.global_lag_grid_velocity_mismatch_field = (
-                self.local_lag_grid_velocity_mismatch_field.view())
-            self.global_lag_grid_forcing_field = self.local_lag_grid_forcing_field.view()
-
-    def _init_local_buffers(self, num_lag_nodes):
-        dim, w = self.grid_dim, self.interp_kernel_width
-        self.local_nearest_eul_grid_index_to_lag_grid = np.empty((dim, num_lag_nodes), dtype=int)
-        self.local_local_eul_grid_support_of_lag_grid = None  # not materialised (fused on device)
-        self.local_interp_weights = np.empty((2 * w,) * dim + (num_lag_nodes,),
-                                             dtype=self.lag_grid_real_t)
-        self.local_lag_grid_flow_velocity_field = np.zeros((dim, num_lag_nodes),
-                                                           dtype=self.lag_grid_real_t)
-        self.local_lag_grid_position_mismatch_field = np.zeros_like(
-            self.local_lag_grid_flow_velocity_field)
-        self.local_lag_grid_velocity_mismatch_field = np.zeros_like(
-            self.local_lag_grid_position_mismatch_field)
-        self.local_lag_grid_forcing_field = np.zeros_like(self.local_lag_grid_velocity_mismatch_field)
-        self.local_lag_grid_position_field = np.zeros_like(self.local_lag_grid_position_mismatch_field)
-        self.local_lag_grid_velocity_field = np.zeros_like(self.local_lag_grid_position_field)
-        # device staging (one block: pos, vel, dpos | flow_vel, dvel, force)
+    def _init_local_buffers(self, num_lag_nodes=None):
+        """(Re)allocate the Lagrangian state.  ``num_lag_nodes`` is accepted for API compatibility
+        (reference :179-236; the restart recipe calls it with the new local size): the arrays here are
+        global-sized, what a rank owns is a mask."""
+        dim, n = self.grid_dim, int(self.global_num_lag_nodes)
         lt = torch_dtype(self.lag_grid_real_t)
-        n = max(int(num_lag_nodes), 1)
-        self._dev_in = torch.zeros((3, dim, n), dtype=lt, device=self.device)
-        self._dev_out = torch.zeros((3, dim, n), dtype=lt, device=self.device)
-        self._dev_nearest = torch.zeros((dim, n), dtype=torch.int64, device=self.device)
-        self._dev_weights = torch.zeros(((2 * w) ** dim, n), dtype=lt, device=self.device)
-        pin = torch.cuda.is_available()
-        self._host_in = torch.zeros((3, dim, n), dtype=lt, pin_memory=pin)
-        self._host_out = torch.zeros((3, dim, n), dtype=lt, pin_memory=pin)
-        self._fetch_index_and_weights = False
+        m = max(n, 1)
+        keep = getattr(self, "_lag", None)
+        # rows: 0 position mismatch, 1 flow velocity at the points, 2 velocity mismatch, 3 force
+        self._lag = torch.zeros((4, dim, m), dtype=lt, device=self.device)
+        if keep is not None and keep.shape == self._lag.shape:
+            self._lag.copy_(keep)  # the mismatch state survives a re-initialisation of the local views
+        self._kin = [torch.zeros((2, dim, m), dtype=lt, device=self.device) for _ in range(2)]
+        pin = self.device.type == "cuda"
+        self._stage = [torch.zeros((2, dim, m), dtype=lt, pin_memory=pin) for _ in range(2)]
+        self._stage_done = [None, None]
+        self._kin_i = 0
+        self._have_kin = False
+        self._owner = torch.zeros(m, dtype=torch.int32, device=self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._flag_host = torch.zeros(1, dtype=torch.int32, pin_memory=pin)
+        self._flag_event = None
+        self._nearest = None
+        self._weights = None
+        self._index_valid = False
+        self._m_dx, self._m_u, self._m_dv, self._m_f = (_Mirror(self._lag[i]) for i in range(4))
+        if keep is not None and keep.shape == self._lag.shape:
+            for m in (self._m_dx, self._m_u, self._m_dv, self._m_f):
+                m.device_newer = True
+        self._handed_out = {}
+        self._owned_idx_cache = None
+        self._params = self.eul_lag_grid_communicator.ib_params(
+            self.lag_grid_real_t, self.virtual_boundary_stiffness_coeff, self.virtual_boundary_damping_coeff)
+        self.local_local_eul_grid_support_of_lag_grid = None  # not materialised (fused on device)
+
+    def _init_global_buffers(self):
+        """reference :179-200; the global buffers are the mirrors themselves"""
+
+    # ---- ownership on the host (diagnostics / API only; the hot path uses the device mask)
+    def _owned_idx(self):
+        if not self._replicated:
+            return None
+        if self._owned_idx_cache is None:
+            if self._have_kin:
+                owner = self._owner.cpu().numpy()
+            else:
+                owner = np.asarray(self.mpi_lagrangian_field_communicator.rank_address)
+            self._owned_idx_cache = np.where(owner == self.mpi_construct.rank)[0]
+        return self._owned_idx_cache
+
+    @property
+    def local_num_lag_nodes(self):
+        idx = self._owned_idx()
+        return int(self.global_num_lag_nodes) if idx is None else int(idx.size)
+
+    @local_num_lag_nodes.setter
+    def local_num_lag_nodes(self, value):  # assigned by the restart recipe; derived here
+        pass
+
+    def _local_get(self, name, mirror):
+        idx = self._owned_idx()
+        if idx is None:
+            return mirror.read()
+        self._flush_handed_out()
+        arr = np.ascontiguousarray(mirror.peek()[:, idx])
+        self._handed_out[name] = (arr, mirror, idx)
+        return arr
+
+    def _local_set(self, mirror, value):
+        idx = self._owned_idx()
+        host = mirror.read()
+        if idx is None:
+            host[...] = value
+        else:
+            host[:, idx] = value
+
+    def _flush_handed_out(self):
+        """local (owned-subset) arrays given to the caller may have been written: fold them back"""
+        for arr, mirror, idx in self._handed_out.values():
+            mirror.read()[:, idx] = arr
+        self._handed_out.clear()
+
+    # global buffers (every rank holds them; the reference only fills them on the master)
+    global_lag_grid_position_mismatch_field = property(
+        lambda self: self._m_dx.read(), lambda self, v: self._m_dx.read().__setitem__(Ellipsis, v))
+    global_lag_grid_velocity_mismatch_field = property(
+        lambda self: self._m_dv.read(), lambda self, v: self._m_dv.read().__setitem__(Ellipsis, v))
+    global_lag_grid_forcing_field = property(
+        lambda self: self._m_f.read(), lambda self, v: self._m_f.read().__setitem__(Ellipsis, v))
+    # rank-local buffers
+    local_lag_grid_position_mismatch_field = property(
+        lambda self: self._local_get("dx", self._m_dx), lambda self, v: self._local_set(self._m_dx, v))
+    local_lag_grid_velocity_mismatch_field = property(
+        lambda self: self._local_get("dv", self._m_dv), lambda self, v: self._local_set(self._m_dv, v))
+    local_lag_grid_forcing_field = property(
+        lambda self: self._local_get("f", self._m_f), lambda self, v: self._local_set(self._m_f, v))
+    local_lag_grid_flow_velocity_field = property(
+        lambda self: self._local_get("u", self._m_u), lambda self, v: self._local_set(self._m_u, v))
+
+    def _local_kinematics(self, row):
+        if not self._have_kin:
+            return np.zeros((self.grid_dim, self.local_num_lag_nodes), dtype=self.lag_grid_real_t)
+        a = self._kin[self._kin_i][row].cpu().numpy()[:, :self.global_num_lag_nodes]
+        idx = self._owned_idx()
+        return a if idx is None else np.ascontiguousarray(a[:, idx])
+
+    local_lag_grid_position_field = property(lambda self: self._local_kinematics(0))
+    local_lag_grid_velocity_field = property(lambda self: self._local_kinematics(1))
+
+    @property
+    def local_nearest_eul_grid_index_to_lag_grid(self):
+        self.fetch_index_and_weights()
+        a = self._nearest.cpu().numpy()[:, :self.global_num_lag_nodes].astype(int)
+        idx = self._owned_idx()
+        return a if idx is None else a[:, idx]
+
+    @property
+    def local_interp_weights(self):
+        self.fetch_index_and_weights()
+        w = self.interp_kernel_width
+        a = self._weights.cpu().numpy().reshape((2 * w,) * self.grid_dim + (-1,))[..., :self.global_num_lag_nodes]
+        idx = self._owned_idx()
+        return a if idx is None else a[..., idx]
 
     def update_buffers(self, global_lag_grid_position_field):
-        """reference :238-276"""
-        comm = self.mpi_lagrangian_field_communicator
-        comm.gather_local_field(global_lag_field=self.global_lag_grid_position_mismatch_field,
-                                local_lag_field=self.local_lag_grid_position_mismatch_field)
-        comm.gather_local_field(global_lag_field=self.global_lag_grid_velocity_mismatch_field,
-                                local_lag_field=self.local_lag_grid_velocity_mismatch_field)
-        comm.map_lagrangian_nodes_based_on_position(global_lag_grid_position_field)
-        update_buffer_flag = self.local_num_lag_nodes != comm.local_num_lag_nodes
-        update_buffer_flag = self.mpi_construct.grid.allreduce(update_buffer_flag, op=MPI.LOR)
-        if update_buffer_flag:
-            self.local_num_lag_nodes = comm.local_num_lag_nodes
-            self._init_local_buffers(self.local_num_lag_nodes)
-            comm.scatter_global_field(local_lag_field=self.local_lag_grid_position_mismatch_field,
-                                      global_lag_field=self.global_lag_grid_position_mismatch_field)
-            comm.scatter_global_field(local_lag_field=self.local_lag_grid_velocity_mismatch_field,
-                                      global_lag_field=self.global_lag_grid_velocity_mismatch_field)
+        """reference :238-276.  The device state needs no migration (see the module docstring); this
+        refreshes the host-side ownership map that the ``local_*`` views follow."""
+        self._flush_handed_out()
+        if not self.assume_data_locality:
+            self.mpi_lagrangian_field_communicator.map_lagrangian_nodes_based_on_position(
+                global_lag_grid_position_field)
+        self._owned_idx_cache = None
 
-    # ---- the three pointwise kernels keep their reference names (host numpy views)
+    # ---- the three pointwise kernels keep their reference names (host numpy arrays)
     @staticmethod
     def compute_lag_grid_velocity_mismatch_field(lag_grid_velocity_mismatch_field,
                                                  lag_grid_flow_velocity_field,
@@ -186,65 +332,113 @@ class VirtualBoundaryForcingMPI:
             + virtual_boundary_damping_coeff * lag_grid_velocity_mismatch_field)
 
     # ---------------------------------------------------------------- hot path
+    def _check_domain_flag(self):
+        ev = self._flag_event
+        if ev is not None and ev.query():
+            self._flag_event = None
+            if int(self._flag_host[0]) != 0:
+                logger.error("Lagrangian node is found outside of Eulerian domain!")
+                self.mpi_construct.grid.Abort()
+
+    def _upload_kinematics(self, global_lag_grid_position_field, global_lag_grid_velocity_field):
+        """positions and velocities of all points -> this rank's device copy (master: pinned staging +
+        one async H2D copy; other ranks: NCCL broadcast).  Double buffered: the previous interaction's
+        kernels may still be reading the other copy."""
+        n = int(self.global_num_lag_nodes)
+        self._kin_i ^= 1
+        i = self._kin_i
+        dst = self._kin[i]
+        if (not self._replicated) or self.mpi_construct.rank == self.master_rank:
+            pos = np.asarray(global_lag_grid_position_field)
+            vel = np.asarray(global_lag_grid_velocity_field)
+            if pos.shape != (self.grid_dim, n) or vel.shape != pos.shape:
+                raise RuntimeError(
+                    f"Lagrangian fields must have shape ({self.grid_dim}, {n}); got {pos.shape}, {vel.shape}")
+            if self._stage_done[i] is not None:
+                self._stage_done[i].synchronize()  # the copy that used this staging buffer two calls ago
+            stage = self._stage[i].numpy()
+            if n:
+                np.copyto(stage[0, :, :n], pos, casting="same_kind")
+                np.copyto(stage[1, :, :n], vel, casting="same_kind")
+            dst.copy_(self._stage[i], non_blocking=True)
+            if dst.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._stage_done[i] = ev
+        if self._replicated:
+            dist.broadcast(dst, src=self.master_rank)
+        self._have_kin = True
+        self._index_valid = False
+        self._owned_idx_cache = None
+        return dst
+
     def compute_interaction_force_on_lag_grid(self, local_eul_grid_velocity_field,
                                               global_lag_grid_position_field,
                                               global_lag_grid_velocity_field):
-        """reference :333-406"""
-        if not self.assume_data_locality:
-            self.update_buffers(global_lag_grid_position_field=global_lag_grid_position_field)
-            comm = self.mpi_lagrangian_field_communicator
-            comm.scatter_global_field(local_lag_field=self.local_lag_grid_position_field,
-                                      global_lag_field=global_lag_grid_position_field)
-            comm.scatter_global_field(local_lag_field=self.local_lag_grid_velocity_field,
-                                      global_lag_field=global_lag_grid_velocity_field)
-        else:
-            self.local_lag_grid_position_field = global_lag_grid_position_field.view()
-            self.local_lag_grid_velocity_field = global_lag_grid_velocity_field.view()
-
-        n = int(self.local_num_lag_nodes)
-        if n > 0:
-            st = Staged(self.device)
-            u = st(local_eul_grid_velocity_field)
-            hin = self._host_in.numpy()
-            hin[0, :, :n] = self.local_lag_grid_position_field
-            hin[1, :, :n] = self.local_lag_grid_velocity_field
-            hin[2, :, :n] = self.local_lag_grid_position_mismatch_field
-            self._dev_in.copy_(self._host_in, non_blocking=True)
-            comm_k = self.eul_lag_grid_communicator
-            self._params = comm_k.ib_params(self.lag_grid_real_t,
-                                            self.virtual_boundary_stiffness_coeff,
-                                            self.virtual_boundary_damping_coeff)
-            din, dout = self._dev_in, self._dev_out
-            nn = din.shape[-1]
-            if nn != n:
-                raise RuntimeError("local Lagrangian buffer size mismatch")
-            comm_k.interact(self._params, n, u, din[0], din[1], din[2], self._dev_nearest,
-                            self._dev_weights if self._fetch_index_and_weights else None,
-                            dout[0], dout[1], dout[2])
-            self._host_out.copy_(dout, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            hout = self._host_out.numpy()
-            self.local_lag_grid_flow_velocity_field[...] = hout[0, :, :n]
-            self.local_lag_grid_velocity_mismatch_field[...] = hout[1, :, :n]
-            self.local_lag_grid_forcing_field[...] = hout[2, :, :n]
-            if self._fetch_index_and_weights:
-                self.fetch_index_and_weights()
-
-        if not self.assume_data_locality:
-            self.mpi_lagrangian_field_communicator.gather_local_field(
-                global_lag_field=self.global_lag_grid_forcing_field,
-                local_lag_field=self.local_lag_grid_forcing_field)
-
-    def fetch_index_and_weights(self):
-        """Mirror nearest indices / interpolation weights of the last interaction to
-        the host buffers (off the hot path; the reference materialises them every call)."""
-        n = int(self.local_num_lag_nodes)
+        """reference :333-406: nearest index, weights, E->L interpolation, velocity mismatch and penalty
+        force in one launch over the points this rank owns; no host synchronisation."""
+        self._check_domain_flag()
+        self._flush_handed_out()
+        n = int(self.global_num_lag_nodes)
+        kin = self._upload_kinematics(global_lag_grid_position_field, global_lag_grid_velocity_field)
         if n == 0:
             return
-        self.local_nearest_eul_grid_index_to_lag_grid[...] = self._dev_nearest.cpu().numpy()[:, :n]
-        w = self.interp_kernel_width
-        self.local_interp_weights[...] = self._dev_weights.cpu().numpy().reshape(
-            (2 * w,) * self.grid_dim + (-1,))[..., :n]
+        st = Staged(self.device)
+        u = st(local_eul_grid_velocity_field)
+        self._last_u = u
+        stream = current_stream_ptr(self.device)
+        comm_k = self.eul_lag_grid_communicator
+        owner = None
+        if not self.assume_data_locality:
+            _lib.check(self.lib, self.lib.sb200_ib_rank_address(
+                _lib.dtype_code(self.lag_grid_real_t), self.grid_dim, n, dptr(kin[0]), self._coord_shift,
+                self._sub_dx, self._topo, dptr(self._owner), dptr(self._flag), stream))
+            if self._flag_event is None and self._flag_host.is_pinned():
+                self._flag_host.copy_(self._flag, non_blocking=True)
+                self._flag_event = torch.cuda.Event()
+                self._flag_event.record()
+            owner = self._owner if self._replicated else None
+        self._m_dx.before_device_read()
+        want_index = self._fetch_index_and_weights
+        if want_index:
+            self._ensure_index_buffers()
+        lag = self._lag
+        _lib.check(self.lib, self.lib.sb200_ib_interact_owned(
+            ctypes.byref(comm_k.grid), ctypes.byref(self._params), n, dptr(u), dptr(kin[0]), dptr(kin[1]),
+            dptr(lag[0]), dptr(self._nearest) if want_index else None,
+            dptr(self._weights) if want_index else None, dptr(lag[1]), dptr(lag[2]), dptr(lag[3]),
+            dptr(owner), int(self.mpi_construct.rank), stream))
+        self._index_valid = want_index
+        if self._replicated:
+            dist.all_reduce(lag[1:4])
+        for m in (self._m_u, self._m_dv, self._m_f):
+            m.after_device_write()
+
+    def _ensure_index_buffers(self):
+        if self._nearest is None:
+            dim, w = self.grid_dim, self.interp_kernel_width
+            m = self._lag.shape[-1]
+            self._nearest = torch.zeros((dim, m), dtype=torch.int64, device=self.device)
+            self._weights = torch.zeros(((2 * w) ** dim, m), dtype=self._lag.dtype, device=self.device)
+
+    def fetch_index_and_weights(self):
+        """Nearest indices / interpolation weights of the last interaction (off the hot path: the
+        reference materialises them every call, here they are recomputed from the device copy of the
+        positions when somebody asks)."""
+        if self._index_valid or not self._have_kin:
+            self._ensure_index_buffers()
+            return
+        self._ensure_index_buffers()
+        n = int(self.global_num_lag_nodes)
+        kin = self._kin[self._kin_i]
+        scratch = torch.zeros_like(self._lag[1])
+        # (the interpolated values go to a scratch array; the velocity field of the last interaction
+        # only provides a valid pointer)
+        _lib.check(self.lib, self.lib.sb200_ib_interact_owned(
+            ctypes.byref(self.eul_lag_grid_communicator.grid), ctypes.byref(self._params), n,
+            dptr(self._last_u), dptr(kin[0]), None, None, dptr(self._nearest), dptr(self._weights),
+            dptr(scratch), None, None, None, 0, current_stream_ptr(self.device)))
+        self._index_valid = True
 
     def compute_interaction_force_on_eul_and_lag_grid(self, local_eul_grid_forcing_field,
                                                       local_eul_grid_velocity_field,
@@ -256,10 +450,14 @@ class VirtualBoundaryForcingMPI:
                                                    global_lag_grid_velocity_field)
         st = Staged(self.device)
         f = st(local_eul_grid_forcing_field, out=True)
-        n = int(self.local_num_lag_nodes)
+        n = int(self.global_num_lag_nodes)
         comm_k = self.eul_lag_grid_communicator
         if n > 0:
-            comm_k.spread(self._params, n, f, self._dev_out[2], self._dev_in[0])
+            kin = self._kin[self._kin_i]
+            _lib.check(self.lib, self.lib.sb200_ib_spread_owned(
+                ctypes.byref(comm_k.grid), ctypes.byref(self._params), n, dptr(f), dptr(self._lag[3]),
+                dptr(kin[0]), dptr(self._owner) if self._replicated else None, int(self.mpi_construct.rank),
+                current_stream_ptr(self.device)))
         comm_k.eulerian_grid_ghost_sum(local_field=f)
         st.finish()
 
@@ -274,9 +472,16 @@ class VirtualBoundaryForcingMPI:
             global_lag_grid_position_field, global_lag_grid_velocity_field)
 
     def time_step(self, dt):
-        """reference :452-459 (O(n) host update of the mirrored mismatch state)"""
-        self.update_lag_grid_position_mismatch_field_via_euler_forward(
-            lag_grid_position_mismatch_field=self.local_lag_grid_position_mismatch_field,
-            lag_grid_velocity_mismatch_field=self.local_lag_grid_velocity_mismatch_field,
-            dt=dt)
+        """reference :452-459: position mismatch += dt * velocity mismatch, on the device, for all points
+        (every rank holds the all-reduced velocity mismatch)"""
+        self._flush_handed_out()
+        self._m_dx.before_device_read()
+        self._m_dv.before_device_read()
+        n = int(self.global_num_lag_nodes)
+        if n > 0:
+            count = self._lag[0].numel()
+            _lib.check(self.lib, self.lib.sb200_ib_update_position_mismatch(
+                _lib.dtype_code(self.lag_grid_real_t), dptr(self._lag[0]), dptr(self._lag[2]), count,
+                float(dt), current_stream_ptr(self.device)))
+            self._m_dx.after_device_write()
         self.time += dt

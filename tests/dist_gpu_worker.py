@@ -123,6 +123,27 @@ def main():
     want = f_glob[:, rank * nzl + gs:rank * nzl + gs + nzl, gs:-gs, gs:-gs]
     assert np.abs(got - want).max() / np.abs(f_glob).max() <= 1e-5
     assert float(np.abs(np.asarray(f_loc)[:, :gs]).max()) == 0.0  # ghosts cleared
+    # device ownership = the reference's integers; the replicated state is the same on every rank
+    assert np.array_equal(vbf._owner.cpu().numpy()[:n_lag], expect_addr)
+    assert vbf.local_num_lag_nodes == int((expect_addr == rank).sum())
+    assert rel(vbf.local_lag_grid_forcing_field, vbf_o.forcing[:, expect_addr == rank]) <= 1e-5
+    # a second interaction after a step, with points that migrated across the slab faces
+    vbf.time_step(0.1)
+    vbf_o.time_step(0.1)
+    pos2 = pos.copy()
+    pos2[2] += 0.6 * float(dx) * np.where(np.arange(n_lag) % 2 == 0, 1.0, -1.0)
+    f_glob[...] = 0
+    vbf_o.compute_interaction_force_on_eul_and_lag_grid(f_glob, u_glob, pos2, vel)
+    vbf.compute_interaction_forcing(local_eul_grid_forcing_field=f_loc, local_eul_grid_velocity_field=u_loc,
+                                    global_lag_grid_position_field=pos2 if rank == 0 else None,
+                                    global_lag_grid_velocity_field=vel if rank == 0 else None)
+    addr2 = ib_oracle.lag_nodes_rank_address(pos2, dx, real_t(dx / 2), mc.local_grid_size, mc.grid_topology)
+    assert np.any(addr2 != expect_addr) and np.array_equal(vbf._owner.cpu().numpy()[:n_lag], addr2)
+    assert rel(vbf.global_lag_grid_forcing_field, vbf_o.forcing) <= 1e-5  # on every rank
+    assert rel(vbf.global_lag_grid_position_mismatch_field, vbf_o.position_mismatch) <= 1e-5
+    got = np.asarray(f_loc)[(slice(None), slice(gs, -gs), slice(gs, -gs), slice(gs, -gs))]
+    want = f_glob[:, rank * nzl + gs:rank * nzl + gs + nzl, gs:-gs, gs:-gs]
+    assert np.abs(got - want).max() / np.abs(f_glob).max() <= 1e-5
 
     dist.barrier()
     if rank == 0:

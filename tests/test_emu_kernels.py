@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from emu_util import call, ptr
+from ib_helpers import rank_address
 from oracle import stencils as st
 from sopht_mpi_b200 import _lib
 
@@ -477,3 +478,61 @@ def test_fused_vorticity_update_on_virtual_z_slabs(real_t):
              None)
         inner = (slice(None), slice(gs, -gs))
         assert _rel(out[inner], ref[:, lo + gs:lo + gs + nzl]) < _tol(real_t)
+
+
+def test_device_rank_ownership_against_reference_golden():
+    """the ownership kernel gives the integers of the reference's
+    _compute_lag_nodes_rank_address (tests/golden/ownership.npz), any topology, both dtypes."""
+    o = np.load(os.path.join(GOLDEN, "ownership.npz"))
+    for t in ("f64", "f32"):
+        for d in ("3", "2"):
+            addr, flag = rank_address(call, ptr, o[f"pos{d}_{t}"], o["dx"][()], o["shift"][()],
+                                                o["local" + d], o["topo" + d])
+            assert np.array_equal(addr, o[f"addr{d}_{t}"]) and flag == 0
+    # a point beyond the last block raises the flag (the reference aborts)
+    pos = o["pos3_f64"].copy()
+    pos[0, 0] = float(o["dx"][()]) * o["local3"][2] * o["topo3"][2] * 1.5
+    _, flag = rank_address(call, ptr, pos, o["dx"][()], o["shift"][()], o["local3"], o["topo3"])
+    assert flag == 1
+
+
+@pytest.mark.parametrize("lag_t", [np.float64, np.float32], ids=["lag64", "lag32"])
+def test_owner_filtered_ib_kernels_assemble_the_global_result(lag_t):
+    """The replicated-state scheme of VirtualBoundaryForcingMPI: every virtual rank runs the
+    interaction on the points it owns and writes zeros elsewhere; the SUM over the ranks equals the
+    single-rank arrays, and the owner-filtered spreading contributions add up to the full spreading."""
+    real_t = np.float32
+    rng = np.random.default_rng(5)
+    dim, gs, w, n_local, n = 3, 2, 2, 12, 40
+    dx, shift = real_t(1.0 / n_local), real_t(0.5 / n_local)
+    g = _lib.make_grid(dim, real_t, gs, (n_local,) * dim, [1] * 6)
+    p = _lib.IBParams()
+    p.lag_dtype, p.kernel_type, p.width = _lib.dtype_code(lag_t), 0, w
+    p.dx, p.coord_shift, p.stiffness, p.damping = float(dx), float(shift), -2.0, -0.3
+    pos = (0.2 + 0.6 * rng.uniform(size=(dim, n))).astype(lag_t)
+    vel = rng.uniform(size=(dim, n)).astype(lag_t)
+    dpos = rng.uniform(size=(dim, n)).astype(lag_t)
+    eul = rng.uniform(size=(dim,) + (n_local + 2 * gs,) * dim).astype(real_t)
+    owner = rng.integers(0, 3, size=n).astype(np.int32)
+
+    def interact(owner_arr, rank):
+        u, dv, f = (np.full((dim, n), 9.0, lag_t) for _ in range(3))
+        call("sb200_ib_interact_owned", ctypes.byref(g), ctypes.byref(p), n, ptr(eul), ptr(pos), ptr(vel),
+             ptr(dpos), None, None, ptr(u), ptr(dv), ptr(f), ptr(owner_arr) if owner_arr is not None else None,
+             rank, None)
+        return u, dv, f
+
+    full = interact(None, 0)
+    parts = [interact(owner, r) for r in range(3)]
+    for k in range(3):
+        assert np.array_equal(sum(part[k] for part in parts), full[k])
+        for r in range(3):
+            assert np.all(parts[r][k][:, owner != r] == 0)
+    spread_full = np.zeros_like(eul)
+    call("sb200_ib_spread_owned", ctypes.byref(g), ctypes.byref(p), n, ptr(spread_full), ptr(full[2]), ptr(pos),
+         None, 0, None)
+    acc = np.zeros_like(eul)
+    for r in range(3):
+        call("sb200_ib_spread_owned", ctypes.byref(g), ctypes.byref(p), n, ptr(acc), ptr(full[2]), ptr(pos),
+             ptr(owner), r, None)
+    assert _rel(acc, spread_full) < 1e-6

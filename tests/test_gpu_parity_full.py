@@ -494,3 +494,104 @@ def test_ghost_sum_with_virtual_ranks_on_one_gpu(cuda, real_t):
         want = ref[:, r * nzl + gs:r * nzl + gs + nzl]
         assert (out[:, gs:-gs] - want).abs().max().item() <= tol, r
         assert float(out[:, :gs].abs().max()) == 0.0 and float(out[:, -gs:].abs().max()) == 0.0
+
+
+# -------------------------------------------------------------- device-resident Lagrangian state
+def test_device_rank_ownership_on_gpu_against_reference_golden(cuda):
+    """SURVEY L1 on the GPU: sb200_ib_rank_address gives the integers of the reference's
+    _compute_lag_nodes_rank_address (tests/golden/ownership.npz, produced by the reference function)."""
+    from ib_helpers import rank_address
+    from sopht_mpi_b200 import _lib
+    from sopht_mpi_b200.utils.device import dptr
+
+    lib = _lib.load()
+    o = np.load(os.path.join(os.path.dirname(__file__), "golden", "ownership.npz"))
+
+    def call(name, *a):
+        _lib.check(lib, getattr(lib, name)(*a))
+
+    to_dev = lambda a: torch.from_numpy(a).to(cuda)  # noqa: E731
+    to_host = lambda t: t.cpu().numpy()  # noqa: E731
+    for t in ("f64", "f32"):
+        for d in ("3", "2"):
+            addr, flag = rank_address(call, dptr, o[f"pos{d}_{t}"], o["dx"][()], o["shift"][()], o["local" + d],
+                                      o["topo" + d], to_dev, to_host)
+            assert np.array_equal(addr, o[f"addr{d}_{t}"]) and flag == 0
+    # many random points incl. block boundaries, against the host twin of the reference expression
+    rng = np.random.default_rng(2)
+    dx, local, topo = np.float32(1.0 / 96), np.array([12, 48, 96]), np.array([8, 2, 1])
+    shift = np.float32(dx / 2)
+    pos = rng.uniform(0.0, 1.0, size=(3, 20000))
+    pos[2] = rng.uniform(0.0, 1.0, size=20000)
+    k = rng.integers(0, 8, size=2000)
+    pos[2, :2000] = k * float(dx) * 12 + float(shift)  # exactly on slab boundaries
+    want = ib_oracle.lag_nodes_rank_address(pos, dx, shift, local, topo)
+    got, flag = rank_address(call, dptr, pos, dx, shift, local, topo, to_dev, to_host)
+    assert np.array_equal(got, want) and flag == 0
+
+
+def test_virtual_boundary_forcing_host_mirrors_follow_the_device(cuda):
+    """The reference keeps the Lagrangian state in host arrays that callers read, write in place and
+    assign (test_virtual_boundary_forcing_mpi_3d.py:1104-1109, the restart recipe); here they are lazy
+    mirrors of device arrays: every access pattern must see reference semantics."""
+    from sopht_mpi_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcingMPI
+
+    real_t, n_local, gs, dim = np.float64, 16, 2, 3
+    mc, _ = _construct((n_local,) * 3, real_t)
+    dx = real_t(1.0 / n_local)
+    rng = np.random.default_rng(9)
+    pos = 0.25 + 0.5 * rng.uniform(size=(dim, 33))
+    vel = rng.uniform(size=(dim, 33))
+    k, c = -3.0, -0.5
+    vbf = VirtualBoundaryForcingMPI(mpi_construct=mc, ghost_size=gs, virtual_boundary_stiffness_coeff=k,
+                                    virtual_boundary_damping_coeff=c, grid_dim=dim, dx=dx,
+                                    global_lag_grid_position_field=pos)
+    ora = ib_oracle.VirtualBoundaryForcingOracle(k, c, dim, dx, real_t, np.float64, gs)
+    assert vbf.local_num_lag_nodes == 33 and vbf.global_num_lag_nodes == 33
+    u_h = rng.uniform(size=(dim,) + (n_local + 2 * gs,) * dim)
+    u = torch.from_numpy(u_h).to(cuda)
+    f = torch.zeros_like(u)
+    f_h = np.zeros_like(u_h)
+    # 1. attribute assignment of the state, then a step (reference test :1104-1109)
+    dpos0 = 0.01 * rng.uniform(size=(dim, 33))
+    vbf.local_lag_grid_position_mismatch_field = dpos0.copy()
+    ora._ensure(33)
+    ora.position_mismatch[...] = dpos0
+    held = vbf.global_lag_grid_forcing_field  # an IO object would keep this reference
+    for step in range(3):
+        vbf.compute_interaction_forcing(local_eul_grid_forcing_field=f, local_eul_grid_velocity_field=u,
+                                        global_lag_grid_position_field=pos, global_lag_grid_velocity_field=vel)
+        f_h[...] = 0
+        ora.compute_interaction_force_on_eul_and_lag_grid(f_h, u_h, pos, vel)
+        assert _rel(held, ora.forcing) <= 1e-12  # refreshed without being asked for again
+        assert _rel(f.cpu().numpy(), f_h) <= 1e-12
+        vbf.time_step(0.05)
+        ora.time_step(0.05)
+        last_pos = pos
+        pos = pos + 0.002  # the body moves: fresh kinematics every interaction
+        if step == 1:  # 2. in-place write through a temporary reference
+            vbf.local_lag_grid_position_mismatch_field[...] *= 0.5
+            ora.position_mismatch[...] *= 0.5
+    assert _rel(vbf.local_lag_grid_position_mismatch_field, ora.position_mismatch) <= 1e-12
+    assert _rel(vbf.global_lag_grid_velocity_mismatch_field, ora.velocity_mismatch) <= 1e-12
+    assert _rel(vbf.local_lag_grid_flow_velocity_field, ora.flow_velocity) <= 1e-12
+    assert np.array_equal(vbf.local_nearest_eul_grid_index_to_lag_grid, ora.nearest)
+    assert _rel(vbf.local_interp_weights, ora.weights) <= 1e-12
+    assert np.array_equal(vbf.local_lag_grid_position_field, last_pos)
+    assert vbf.time == pytest.approx(0.15)
+    # 3. restart recipe: re-map, re-initialise the local buffers, scatter the global state back
+    saved = vbf.global_lag_grid_position_mismatch_field.copy()
+    comm = vbf.mpi_lagrangian_field_communicator
+    comm.map_lagrangian_nodes_based_on_position(pos)
+    vbf.local_num_lag_nodes = comm.local_num_lag_nodes
+    vbf._init_local_buffers(vbf.local_num_lag_nodes)
+    comm.scatter_global_field(local_lag_field=vbf.local_lag_grid_position_mismatch_field, global_lag_field=saved)
+    vbf.time_step(0.0)
+    assert np.array_equal(vbf.local_lag_grid_position_mismatch_field, saved)
+    # 4. a point outside the domain is reported (the reference aborts)
+    bad = pos.copy()
+    bad[0, 0] = 1.7
+    vbf.compute_interaction_force_on_lag_grid(u, bad, vel)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        vbf.compute_interaction_force_on_lag_grid(u, pos, vel)
