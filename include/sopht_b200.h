@@ -62,6 +62,18 @@ int sb200_add_fixed_val(int dtype, void* field, int ncomp, int64_t count, const 
  * (3D: omega(3), F(3); 2D: omega scalar, F(2)) */
 int sb200_update_vorticity_from_velocity_forcing(const sb200_grid_t* g, void* vorticity,
                                                  const void* velocity_forcing, double prefactor, void* stream);
+/* The same update for a forcing field that is zero almost everywhere (immersed-boundary forcing):
+ * omega is only read and written where curl(F) != 0, and `tile_flags` (device bytes,
+ * sb200_tile_flag_count(g) of them, zero-initialised once by the caller) records which 256-cell
+ * blocks of the padded array hold a non-zero F.  sb200_clear_flagged_tiles zeroes `field` on the
+ * flagged blocks and clears the flags: the `set_field(F, 0)` that ends the reference step
+ * (simulator/flow/flow_simulators_mpi_3d.py:422-424, flow_simulators_mpi_2d.py:291-293) at a cost
+ * proportional to the support of F. */
+int64_t sb200_tile_flag_count(const sb200_grid_t* g);
+int sb200_update_vorticity_from_sparse_forcing(const sb200_grid_t* g, void* vorticity,
+                                               const void* velocity_forcing, double prefactor,
+                                               void* tile_flags, void* stream);
+int sb200_clear_flagged_tiles(const sb200_grid_t* g, void* field, int ncomp, void* tile_flags, void* stream);
 /* stencil_ops_3d/curl_mpi_3d.py:29-194; 2D: stencil_ops_2d/outplane_field_curl_mpi_2d.py:10-141 */
 int sb200_curl(const sb200_grid_t* g, void* curl, const void* field, double prefactor, void* stream);
 /* stencil_ops_3d/diffusion_flux_mpi_3d.py:35-192 (scalar field) */

@@ -57,6 +57,9 @@ PROTOTYPES = {
     "sb200_update_vorticity_from_velocity_forcing": (c_int, [_G, _V, _V, c_double, _V]),
     "sb200_curl": (c_int, [_G, _V, _V, c_double, _V]),
     "sb200_diffusion_flux": (c_int, [_G, _V, _V, c_double, _V]),
+    "sb200_tile_flag_count": (c_int64, [_G]),
+    "sb200_update_vorticity_from_sparse_forcing": (c_int, [_G, _V, _V, c_double, _V, _V]),
+    "sb200_clear_flagged_tiles": (c_int, [_G, _V, c_int, _V, _V]),
     "sb200_diffusion_timestep": (c_int, [_G, _V, c_int, _V, c_double, _V]),
     "sb200_advection_flux_eno3": (c_int, [_G, _V, _V, _V, c_double, _V]),
     "sb200_advection_timestep_eno3": (c_int, [_G, _V, c_int, _V, _V, c_double, _V]),

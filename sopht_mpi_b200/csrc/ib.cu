@@ -385,8 +385,30 @@ struct ClearGhostOp {
 extern "C" int sb200_clear_ghost_cells(const sb200_grid_t* gr, void* field, int ncomp, void* stream) {
   SbGeom g;
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  if (g.gs == 0) return 0;
+  // only the six ghost slabs are visited (disjoint boxes: x slabs, y slabs between them, z slabs in
+  // the middle), not every cell of the field
+  SbBoxes b;
+  b.n = 0;
+  auto add = [&](int z0, int z1, int y0, int y1, int x0, int x1) {
+    const int lo[3] = {z0, y0, x0}, hi[3] = {z1, y1, x1};
+    for (int d = 0; d < 3; ++d) {
+      b.lo[b.n][d] = lo[d];
+      b.hi[b.n][d] = hi[d];
+    }
+    ++b.n;
+  };
+  const int gs = g.gs;
+  add(0, g.mz, 0, g.my, 0, gs);
+  add(0, g.mz, 0, g.my, g.mx - gs, g.mx);
+  add(0, g.mz, 0, gs, gs, g.mx - gs);
+  add(0, g.mz, g.my - gs, g.my, gs, g.mx - gs);
+  if (g.dim == 3) {
+    add(0, gs, gs, g.my - gs, gs, g.mx - gs);
+    add(g.mz - gs, g.mz, gs, g.my - gs, gs, g.mx - gs);
+  }
   SB_DISPATCH_DTYPE(gr->dtype,
-                    return sb_launch_cells(g, ClearGhostOp<T>{(T*)field, ncomp}, stream, "clear_ghost"));
+                    return sb_launch_boxes(g, b, ClearGhostOp<T>{(T*)field, ncomp}, stream, "clear_ghost"));
 }
 
 // field[gs:2gs] += from_prev ; field[-2gs:-gs] += from_next   (z slabs of gs padded planes,

@@ -48,8 +48,13 @@ struct SbLines {
   long long s1_hi = 0;
   int qs = 4;
   long long bstride = 0;
+  // grouped lines (tile-contiguous layout of the fused z pass): line i sits at (i & (2^gsh - 1)) inside
+  // group i >> gsh, groups are s_grp elements apart.  gsh = 31: plain (line i at element i).
+  int gsh = 31;
+  long long s_grp = 0;
   SB_HD long long base(int i, int o1, int o2) const {
-    return i + (long long)(o1 & ((1 << o1_shift) - 1)) * s1 + (long long)(o1 >> o1_shift) * s1_hi + o2 * s2;
+    return (i & ((1u << gsh) - 1)) + (long long)(i >> gsh) * s_grp +
+           (long long)(o1 & ((1 << o1_shift) - 1)) * s1 + (long long)(o1 >> o1_shift) * s1_hi + o2 * s2;
   }
   SB_HD long long point(int t, int p, int Tn) const {
     return (long long)(p >> qs) * bstride + (long long)(t + (p & ((1 << qs) - 1)) * Tn) * pt;
@@ -507,6 +512,110 @@ __global__ void __launch_bounds__(LINES*((1 << LOG2N) / SB_FFT_P32), sb_p32_min_
   }
 }
 
+// ------------------------------------------------------ fused z pass, persistent + bulk-copy prefetch
+// The same transform as sb_fft_strided32_kernel<MODE 1> (forward FFT of the zero-padded z line, x real
+// Green's spectrum, inverse FFT, first half kept, in place) on a TILE-CONTIGUOUS layout
+//     Bt[c][kx group][ky][z][8 lines]            (one tile = nz x 8 complex = 16 / 32 KB contiguous)
+// so that a whole tile moves with ONE bulk asynchronous copy (cp.async.bulk, the 1D TMA path, completion
+// on an mbarrier).  Blocks are persistent: while a tile is transformed, the next tile of the block is
+// already landing in shared memory, so the HBM latency that the one-tile-per-block kernel exposes at
+// the start of every block (2-4 resident blocks per SM cannot hide it) leaves the critical path.
+// Tiles are numbered (ky, kx group, component) with the component fastest: the three components of one
+// (kx group, ky) are in flight together and share the Green's table rows in L2.
+#ifndef SB200_EMU
+SB_D unsigned sb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SB_D void sb_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// arm the barrier with the byte count and start the copy (one thread)
+SB_D void sb_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   sb_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(sb_smem_u32(bar))
+               : "memory");
+}
+SB_D void sb_mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(sb_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+#else
+SB_D void sb_mbar_init(unsigned long long*, unsigned) {}
+SB_D void sb_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) {
+  memcpy(smem_dst, gsrc, bytes);
+}
+SB_D void sb_mbar_wait(unsigned long long*, unsigned) {}
+#endif
+
+constexpr int sb_zconv_blocks(int log2n) { return log2n >= 10 ? 2 : 4; }
+
+template <int LOG2N>
+__global__ void __launch_bounds__(8 * ((1 << LOG2N) / SB_FFT_P32), sb_zconv_blocks(LOG2N))
+    sb_fft_zconv32_kernel(C2<float>* B, int ntiles, int ncomp, int ng, int nky, const C2<float>* __restrict__ tw,
+                          const float* __restrict__ g2, int n1_full) {
+  using FC = SbFft32C<LOG2N>;
+  constexpr int PT = SB_FFT_P32, Tn = FC::Tn, LINES = 8, NT = LINES * Tn, NZ = FC::n / 2;
+  constexpr unsigned TILE = NZ * LINES;  // complex elements of a tile
+  SB_DYN_SMEM(smem_raw);
+  C2<float>* sm = reinterpret_cast<C2<float>*>(smem_raw);  // exchange buffer [npad][8]
+  C2<float>* sin = sm + LINES * FC::npad;                  // landing buffer of the tile [nz][8]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sin + TILE);
+  const int tid = threadIdx.x, l = tid & (LINES - 1), t = tid >> 3;
+  auto tile_offset = [&](int tile, int& kxg, int& ky) {
+    const int c = tile % ncomp, r = tile / ncomp;
+    kxg = r % ng;
+    ky = r / ng;
+    return (((long long)c * ng + kxg) * nky + ky) * (long long)TILE;
+  };
+  if (tid == 0) sb_mbar_init(bar, 1);
+  __syncthreads();
+  int tile = blockIdx.x, kxg = 0, ky = 0;
+  unsigned phase = 0;
+  if (tid == 0 && tile < ntiles) sb_bulk_load(sin, B + tile_offset(tile, kxg, ky), TILE * sizeof(C2<float>), bar);
+  __syncthreads();
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long off = tile_offset(tile, kxg, ky);
+    sb_mbar_wait(bar, phase);
+    phase ^= 1u;
+    C2<float> v[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+      v[p] = p < PT / 2 ? sin[(t + p * Tn) * LINES + l] : C2<float>{0.f, 0.f};
+    __syncthreads();  // the landing buffer has been consumed (and the previous tile's re-reads are done)
+    {
+      const int next = tile + gridDim.x;
+      int a, b;
+      if (tid == 0 && next < ntiles) sb_bulk_load(sin, B + tile_offset(next, a, b), TILE * sizeof(C2<float>), bar);
+    }
+    sb_fft32_forward_c<float, LOG2N, LINES, true>(v, t, tw, sm + l);
+    {
+      const int m1 = ky <= (n1_full >> 1) ? ky : n1_full - ky;
+      const float4* src = reinterpret_cast<const float4*>(g2) + (((long long)m1 * ng + kxg) * NT + tid) * (PT / 4);
+#pragma unroll
+      for (int k = 0; k < PT / 4; ++k) {
+        const float4 gv = src[k];
+        v[4 * k] = cscale(v[4 * k], gv.x);
+        v[4 * k + 1] = cscale(v[4 * k + 1], gv.y);
+        v[4 * k + 2] = cscale(v[4 * k + 2], gv.z);
+        v[4 * k + 3] = cscale(v[4 * k + 3], gv.w);
+      }
+    }
+    sb_fft32_inverse_c<float, LOG2N, LINES, false>(v, t, tw, sm + l);
+    C2<float>* out = B + off + (t * LINES + l);
+#pragma unroll
+    for (int p = 0; p < PT / 2; ++p) out[(long long)p * Tn * LINES] = v[p];
+  }
+}
+
 // Re(spectrum) * scale -> mirror-compressed table
 template <typename T>
 struct GreensExtractOp {
@@ -558,6 +667,9 @@ struct SbFftState {
   size_t bytes = 0;
   int kb = 0;  // ky block size of the B layout (power of two, multiple of 2ny/16, divides 2ny)
   int kxl = 0; // x-slab decomposition: kx bins per rank (ceil((nx + 1) / nranks))
+  // tile-contiguous layout of B + persistent bulk-copy z kernel (float, 3D, 2nz = 512 / 1024)
+  bool zconv = false;
+  int ng = 0;  // kx groups of 8 lines
   // optional per-launch timing (sb200_poisson_set_profiling): events around the five launches
   bool profile = false, have_times = false;
 #ifndef SB200_EMU
@@ -763,6 +875,47 @@ static int launch_strided(const SbFftPlan& plan, const C2<T>* in, const SbLines&
   return launch_strided_c<T, MODE, 0>(plan, in, lin, out, lout, tw, gt, stream);
 }
 
+template <int LOG2N>
+static int launch_zconv32(C2<float>* B, int ncomp, int ng, int nky, const C2<float>* tw, const float* g2,
+                          int n1_full, void* stream) {
+  using FC = SbFft32C<LOG2N>;
+  constexpr int NT = 8 * FC::Tn;
+  const size_t smem = sizeof(C2<float>) * (size_t)(8 * FC::npad + 8 * (FC::n / 2)) + 16;
+  SB_KERNEL_ATTR_SMEM((sb_fft_zconv32_kernel<LOG2N>), smem);
+  const long long ntiles = (long long)ncomp * ng * nky;
+  long long resident = 148LL * sb_zconv_blocks(LOG2N);
+#ifndef SB200_EMU
+  {
+    static long long cached = 0;
+    if (cached == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_fft_zconv32_kernel<LOG2N>, NT, smem);
+      cached = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    }
+    resident = cached;
+  }
+#else
+  resident = 3;  // a few persistent "blocks", several tiles each
+#endif
+  const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+  SB_LAUNCH_COOP((sb_fft_zconv32_kernel<LOG2N>), dim3(grid), dim3(NT), smem, stream, B, (int)ntiles, ncomp, ng, nky,
+                 tw, g2, n1_full);
+  SB_CHECK_LAUNCH("fft_zconv32");
+  return 0;
+}
+template <typename T>
+static int launch_zconv(int log2n, C2<T>* B, int ncomp, int ng, int nky, const C2<T>* tw, const T* g2, int n1_full,
+                        void* stream) {
+  if constexpr (sizeof(T) == 4) {
+    if (log2n == 9) return launch_zconv32<9>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
+    if (log2n == 10) return launch_zconv32<10>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
+  }
+  sb_set_error("fft_zconv: unsupported transform length");
+  return -1;
+}
+
 template <typename T>
 static int fft_create_t(sb200_poisson* p, void* stream) {
   auto* st = new SbFftState<T>();
@@ -795,12 +948,22 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   // y and z passes on B[c][nz][2ny][kxl]
   st->kxl = p->nranks > 1 ? sb_slab_kxl(nx, p->nranks) : 0;
   const size_t a_bytes = p->nranks == 1 ? sizeof(C2<T>) * 3 * (size_t)(p->dim == 3 ? nz : 1) * ny * P : 0;
+  {
+    const int inner = p->nranks > 1 ? st->kxl : nx + 1;
+    st->ng = (inner + 7) / 8;
+    static const bool env_off = getenv("SB200_ZCONV") && atoi(getenv("SB200_ZCONV")) == 0;
+    st->zconv = !env_off && sizeof(T) == 4 && p->dim == 3 && p->nranks == 1 && (st->pz.log2n == 9 || st->pz.log2n == 10) &&
+                sb_use_p32(1, st->pz.log2n);
+  }
   const size_t b_bytes = p->dim != 3 ? 0
+                         : st->zconv ? sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * 8 * st->ng
                          : p->nranks == 1 ? sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * P
                                           : sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * st->kxl;
   const size_t g_bytes = sizeof(T) * (p->dim == 3 ? (nz + 1) : 1) * (ny + 1) * P;
   if (a_bytes) SB_REQUIRE(SB_DEV_ALLOC(st->A, a_bytes), "fft backend: cannot allocate x-pass buffer");
   if (b_bytes) SB_REQUIRE(SB_DEV_ALLOC(st->B, b_bytes), "fft backend: cannot allocate y-pass buffer");
+  // (the padding lines of the last kx group are transformed along with the others: keep them finite)
+  if (b_bytes && st->zconv) sb_memset_async(st->B, 0, b_bytes, stream);
   SB_REQUIRE(SB_DEV_ALLOC(st->G, g_bytes), "fft backend: cannot allocate Green's table");
   st->bytes = a_bytes + b_bytes + g_bytes;
 
@@ -868,29 +1031,44 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
   st->mark(1, stream);
   SbGreensTable<T> none{nullptr, 0, 0};
   if (p->dim == 3) {
+    if (st->zconv) {
+      // tile-contiguous B: Bt[c][kx group][ky][z][8]; y passes address it through grouped lines
+      const long long NZ = nz, NKY = 2LL * ny, tile = NZ * 8;
+      SbLines la{nx + 1, nz, ncomp, (long long)ny * P, (long long)nz * ny * P, P};
+      SbLines lb{nx + 1, nz, ncomp, 8, (long long)st->ng * NKY * tile, tile};
+      lb.gsh = 3;
+      lb.s_grp = NKY * tile;
+      if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
+      st->mark(2, stream);
+      if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * ny, stream))) return e;
+      st->mark(3, stream);
+      if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
+      st->mark(4, stream);
+    } else {
     // y forward: A[c][z][y][kx] -> B[c][kyb][z][ky_in][kx]  (ky = kyb*KB + ky_in, see SbLines)
-    const int KB = st->kb, Tny = st->py.threads;
-    int kb_shift = 0, q_shift = 0;
-    while ((1 << kb_shift) < KB) ++kb_shift;
-    while ((Tny << q_shift) < KB) ++q_shift;
-    const long long cstride = 2LL * nz * ny * P;
-    SbLines la{nx + 1, nz, ncomp, (long long)ny * P, (long long)nz * ny * P, P};
-    SbLines lb{nx + 1, nz, ncomp, (long long)KB * P, cstride, P};
-    lb.qs = q_shift;
-    lb.bstride = (long long)nz * KB * P;
-    if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
-    st->mark(2, stream);
-    // z: forward, x Ghat, inverse, in place on B; lines (kx, ky, c), points KB*P apart
-    SbLines lz{nx + 1, 2 * ny, ncomp, P, cstride, (long long)KB * P};
-    lz.o1_shift = kb_shift;
-    lz.s1_hi = (long long)nz * KB * P;
-    SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P, 2 * ny, 0};
-    gt.g2 = st->G2;
-    if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
-    st->mark(3, stream);
-    // y inverse: B -> A
-    if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
-    st->mark(4, stream);
+      const int KB = st->kb, Tny = st->py.threads;
+      int kb_shift = 0, q_shift = 0;
+      while ((1 << kb_shift) < KB) ++kb_shift;
+      while ((Tny << q_shift) < KB) ++q_shift;
+      const long long cstride = 2LL * nz * ny * P;
+      SbLines la{nx + 1, nz, ncomp, (long long)ny * P, (long long)nz * ny * P, P};
+      SbLines lb{nx + 1, nz, ncomp, (long long)KB * P, cstride, P};
+      lb.qs = q_shift;
+      lb.bstride = (long long)nz * KB * P;
+      if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
+      st->mark(2, stream);
+      // z: forward, x Ghat, inverse, in place on B; lines (kx, ky, c), points KB*P apart
+      SbLines lz{nx + 1, 2 * ny, ncomp, P, cstride, (long long)KB * P};
+      lz.o1_shift = kb_shift;
+      lz.s1_hi = (long long)nz * KB * P;
+      SbGreensTable<T> gt{st->G, (long long)(ny + 1) * P, P, 2 * ny, 0};
+      gt.g2 = st->G2;
+      if ((e = launch_strided<T, 1>(st->pz, st->B, lz, st->B, lz, st->twz, gt, stream))) return e;
+      st->mark(3, stream);
+      // y inverse: B -> A
+      if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
+      st->mark(4, stream);
+    }
   } else {
     st->mark(2, stream);
     // 2D: fused forward / multiply / inverse along y, in place on A; lines (kx, -, c)

@@ -149,6 +149,88 @@ struct UpdateVorticityOp {
   }
 };
 
+// ---- forcing update for a forcing field that is zero almost everywhere (immersed-boundary forcing
+// lives within two cells of the Lagrangian points).  Same cells and arithmetic as UpdateVorticityOp,
+// but the read-modify-write of omega is skipped where curl(F) == 0 (omega + 0 == omega), and every
+// block records in `flags` whether its 256 cells hold a non-zero forcing value, so that the `F = 0`
+// that ends the step (flow_simulators_mpi_3d.py:422-424) only has to touch those blocks
+// (sb200_clear_flagged_tiles).  Block (blockIdx.x, z) <-> flag z * gridDim.x + blockIdx.x.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sb_update_vorticity_sparse_kernel(SbGeom g, T* __restrict__ w, const T* __restrict__ f, T p,
+                                      unsigned char* flags) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int z = blockIdx.y;
+  if (idx >= g.plane) return;
+  const int y = (int)(idx / g.mx);
+  const int x = (int)(idx - (long long)y * g.mx);
+  const long long i = (long long)z * g.plane + idx;
+  bool nonzero = f[i] != T(0) || f[i + g.vol] != T(0);
+  if (g.dim == 3) nonzero = nonzero || f[i + 2 * g.vol] != T(0);
+  if (nonzero) flags[(long long)blockIdx.y * gridDim.x + blockIdx.x] = 1;  // (every writer stores 1)
+  if (!g.deep(z, y, x) && !g.written(z, y, x, 1)) return;
+  if (g.dim == 3) {
+    T cx, cy, cz;
+    curl3_at(g, f, i, p, cx, cy, cz);
+    if (cx != T(0)) w[i] += cx;
+    if (cy != T(0)) w[i + g.vol] += cy;
+    if (cz != T(0)) w[i + 2 * g.vol] += cz;
+  } else {
+    const T* fx = f;
+    const T* fy = f + g.vol;
+    const T c = p * (fy[i + 1] - fy[i - 1] - fx[i + g.mx] + fx[i - g.mx]);
+    if (c != T(0)) w[i] += c;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sb_clear_flagged_kernel(SbGeom g, T* __restrict__ f, int ncomp, const unsigned char* __restrict__ flags) {
+  if (!flags[(long long)blockIdx.y * gridDim.x + blockIdx.x]) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.plane) return;
+  const long long i = (long long)blockIdx.y * g.plane + idx;
+  for (int c = 0; c < ncomp; ++c) f[i + c * g.vol] = T(0);
+}
+static inline dim3 sb_tile_grid(const SbGeom& g) { return dim3((unsigned)((g.plane + 255) / 256), (unsigned)g.mz); }
+
+extern "C" int64_t sb200_tile_flag_count(const sb200_grid_t* gr) {
+  SbGeom g;
+  if (sb_make_geom(gr, &g) != 0) return 0;
+  const dim3 grid = sb_tile_grid(g);
+  return (int64_t)grid.x * grid.y;
+}
+extern "C" int sb200_update_vorticity_from_sparse_forcing(const sb200_grid_t* gr, void* vorticity,
+                                                          const void* velocity_forcing, double prefactor,
+                                                          void* tile_flags, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(vorticity && velocity_forcing && tile_flags, "update_vorticity_from_sparse_forcing: null pointer");
+  SB_DISPATCH_DTYPE(gr->dtype, {
+    SB_LAUNCH(sb_update_vorticity_sparse_kernel<T>, sb_tile_grid(g), dim3(256), 0, stream, g, (T*)vorticity,
+              (const T*)velocity_forcing, (T)prefactor, (unsigned char*)tile_flags);
+  });
+  SB_CHECK_LAUNCH("update_vorticity_sparse");
+  return 0;
+}
+extern "C" int sb200_clear_flagged_tiles(const sb200_grid_t* gr, void* field, int ncomp, void* tile_flags,
+                                         void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(field && tile_flags && ncomp >= 1 && ncomp <= 3, "clear_flagged_tiles: bad arguments");
+  SB_DISPATCH_DTYPE(gr->dtype, {
+    SB_LAUNCH(sb_clear_flagged_kernel<T>, sb_tile_grid(g), dim3(256), 0, stream, g, (T*)field, ncomp,
+              (const unsigned char*)tile_flags);
+  });
+  SB_CHECK_LAUNCH("clear_flagged_tiles");
+  const dim3 grid = sb_tile_grid(g);
+  const int e = sb_memset_async(tile_flags, 0, (size_t)grid.x * grid.y, stream);
+  if (e) {
+    sb_set_error("memset: %s", sb_error_string(e));
+    return -2;
+  }
+  return 0;
+}
+
 template <typename T>
 struct CurlOp {
   T* c;

@@ -536,3 +536,35 @@ def test_owner_filtered_ib_kernels_assemble_the_global_result(lag_t):
         call("sb200_ib_spread_owned", ctypes.byref(g), ctypes.byref(p), n, ptr(acc), ptr(full[2]), ptr(pos),
              ptr(owner), r, None)
     assert _rel(acc, spread_full) < 1e-6
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+@pytest.mark.parametrize("sparse", [True, False], ids=["sparse", "dense"])
+def test_sparse_forcing_update_and_flagged_reset(dim, sparse):
+    """sb200_update_vorticity_from_sparse_forcing == the plain update (bit for bit, for a forcing field
+    that is zero almost everywhere as well as for a dense one); sb200_clear_flagged_tiles leaves F == 0
+    and the flags cleared."""
+    real_t = np.float32
+    rng = np.random.default_rng(12)
+    gs = 2
+    n = (10, 37, 45) if dim == 3 else (37, 45)
+    shape = tuple(v + 2 * gs for v in n)
+    g = _lib.make_grid(dim, real_t, gs, n, [1] * (2 * dim))
+    w = rng.uniform(size=((3,) + shape) if dim == 3 else shape).astype(real_t)
+    f = rng.uniform(-1, 1, size=(dim,) + shape).astype(real_t)
+    if sparse:
+        mask = np.zeros(shape, bool)
+        mask[(slice(4, 8),) * dim] = True
+        mask[(-1,) * dim] = True  # a ghost corner cell too
+        f *= mask
+    ref, got = w.copy(), w.copy()
+    call("sb200_update_vorticity_from_velocity_forcing", ctypes.byref(g), ptr(ref), ptr(f), 0.37, None)
+    from emu_util import emu
+
+    count = int(emu().sb200_tile_flag_count(ctypes.byref(g)))
+    flags = np.zeros(count, np.uint8)
+    call("sb200_update_vorticity_from_sparse_forcing", ctypes.byref(g), ptr(got), ptr(f), 0.37, ptr(flags), None)
+    assert np.array_equal(got, ref)
+    assert 0 < flags.sum() and (flags.sum() < count if sparse else flags.sum() == count)
+    call("sb200_clear_flagged_tiles", ctypes.byref(g), ptr(f), dim, ptr(flags), None)
+    assert not f.any() and not flags.any()
