@@ -63,10 +63,10 @@ int sb200_add_fixed_val(int dtype, void* field, int ncomp, int64_t count, const 
 int sb200_update_vorticity_from_velocity_forcing(const sb200_grid_t* g, void* vorticity,
                                                  const void* velocity_forcing, double prefactor, void* stream);
 /* The same update for a forcing field that is zero almost everywhere (immersed-boundary forcing):
- * omega is only read and written where curl(F) != 0, and `tile_flags` (device bytes,
- * sb200_tile_flag_count(g) of them, zero-initialised once by the caller) records which 256-cell
- * blocks of the padded array hold a non-zero F.  sb200_clear_flagged_tiles zeroes `field` on the
- * flagged blocks and clears the flags: the `set_field(F, 0)` that ends the reference step
+ * F is read once to flag the 1024-cell chunks of the padded array that hold a non-zero value
+ * (`tile_flags`: device bytes, sb200_tile_flag_count(g) of them, zero-initialised once by the caller),
+ * omega is only touched on chunks whose stencil reaches a flagged chunk.  sb200_clear_flagged_tiles
+ * zeroes `field` on the flagged chunks and clears the flags: the `set_field(F, 0)` that ends the reference step
  * (simulator/flow/flow_simulators_mpi_3d.py:422-424, flow_simulators_mpi_2d.py:291-293) at a cost
  * proportional to the support of F. */
 int64_t sb200_tile_flag_count(const sb200_grid_t* g);

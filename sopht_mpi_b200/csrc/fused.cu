@@ -13,6 +13,8 @@
 // next plane's omega/u are prefetched into registers while the current one is processed.
 #include "sb200_common.h"
 
+#include <cstdlib>
+
 template <int TY, int TX, int NT>
 struct FusedTile {
   static constexpr int P2 = TX + 4, R2 = (TY + 4) * P2;  // tile + halo 2
@@ -202,6 +204,255 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Float version 2: the same update with vectorised global access and far fewer instructions per cell.
+// A warp owns one row of 64 cells (32 lanes x a strip of 2 cells: 8-byte loads / stores, 256 contiguous
+// bytes per warp), a block R consecutive rows, and the block marches along z.  z neighbours are carried
+// in registers (two planes of history), x neighbours come from the strip itself or from the adjacent
+// lanes (shuffles), and only the y neighbours go through shared memory (5 arrays, double buffered, ONE
+// barrier per plane).  Every thread evaluates all three levels on its own cells: u x omega on the whole
+// block footprint, omega2 on footprint - 1, the result on footprint - 2, so a block stores (R - 4) rows
+// x 60 cells.  Blocks whose footprint lies inside the region written by the reference's interior
+// call skip the per-cell wrapper masks (FAST); the others evaluate them exactly as version 1 does.
+template <int R>
+struct FusedV2 {
+  static constexpr int NT = 32 * R;
+  static constexpr int TXU = 60, TYU = R - 4;        // cells stored per block
+  static constexpr int ROW = 64;                     // floats per row in shared memory
+  static constexpr int ARR = (R + 2) * ROW;          // one array: R rows + a guard row at each end
+  static constexpr int ELEMS = 2 * 5 * ARR;          // double buffered: buf_x, buf_z, omega2 x 3
+};
+
+struct alignas(8) F2 {
+  float x, y;
+};
+SB_D F2 sb_ld2(const float* p) { return *reinterpret_cast<const F2*>(p); }
+SB_D void sb_st2(float* p, F2 v) { *reinterpret_cast<F2*>(p) = v; }
+
+template <int R, bool FAST>
+SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, const float* __restrict__ w,
+                                     const float* __restrict__ u, float p, float d, int zchunk, float* smem) {
+  using FV = FusedV2<R>;
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int x = (int)blockIdx.x * FV::TXU - 2 + 2 * lane;  // first cell of the strip (even)
+  const int y = (int)blockIdx.y * FV::TYU - 2 + row;
+  const int zb = blockIdx.z * zchunk;
+  const int ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
+  const long long vol = g.vol, plane = g.plane;
+  const int zlo = g.phys[0] ? g.gs : 1, zhi = g.phys[1] ? g.mz - g.gs : g.mz - 1;
+  const int zring_lo = g.phys[0] ? g.gs + 1 : 0, zring_hi = g.phys[1] ? g.mz - g.gs - 1 : g.mz;
+  // per-cell (y,x) masks (z invariant): bit0 A, bit1 B, bit2 inside the array, bit3 physical ring
+  int m0 = 6, m1 = 6;
+  bool in0 = true, in1 = true;
+  if (!FAST) {
+    m0 = sb_yx_mask(g, y, x);
+    m1 = sb_yx_mask(g, y, x + 1);
+    in0 = (m0 & 4) != 0;
+    in1 = (m1 & 4) != 0;
+  }
+  // a strip is loaded / stored as one 8-byte access when both cells are inside the array
+  const bool pair = in0 && in1;
+  const long long goff = (long long)y * g.mx + x;
+  const bool st_row = row >= 2 && row < R - 2 && lane >= 1 && lane <= 30;  // cells this thread stores
+  float* sA = smem;  // [parity][array][row + 1][64]
+  const int soff = (row + 1) * FV::ROW + 2 * lane;
+
+  F2 wp[3] = {}, b1[3] = {}, b2xy[2] = {}, q2[3] = {}, q3[3] = {};
+  // zero the guard rows once (rows 0 and R + 1 of every array are only read by the edge rows, whose
+  // results are never stored, but they must not hold NaN patterns that trap nothing: keep them finite)
+  for (int i = threadIdx.x; i < FV::ELEMS; i += FV::NT) smem[i] = 0.f;
+  __syncthreads();
+
+  for (int zf = zb - 2; zf <= ze + 1; ++zf) {
+    const int par = zf & 1;
+    float* sw = sA + par * 5 * FV::ARR;               // written this iteration
+    const float* sr = sA + (par ^ 1) * 5 * FV::ARR;   // written by the previous iteration
+    // ---- plane zf: omega, u -> u x omega
+    F2 wc[3], uc[3];
+    const bool zin = zf >= 0 && zf < g.mz;
+    if (zin && (FAST || pair)) {
+      const long long gi = (long long)zf * plane + goff;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        wc[c] = sb_ld2(w + gi + c * vol);
+        uc[c] = sb_ld2(u + gi + c * vol);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        wc[c] = F2{0.f, 0.f};
+        uc[c] = F2{0.f, 0.f};
+      }
+      if (!FAST && zin) {
+        const long long gi = (long long)zf * plane + goff;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (in0) {
+            wc[c].x = w[gi + c * vol];
+            uc[c].x = u[gi + c * vol];
+          }
+          if (in1) {
+            wc[c].y = w[gi + 1 + c * vol];
+            uc[c].y = u[gi + 1 + c * vol];
+          }
+        }
+      }
+    }
+    F2 b0[3];
+    b0[0] = F2{uc[1].x * wc[2].x - uc[2].x * wc[1].x, uc[1].y * wc[2].y - uc[2].y * wc[1].y};
+    b0[1] = F2{uc[2].x * wc[0].x - uc[0].x * wc[2].x, uc[2].y * wc[0].y - uc[0].y * wc[2].y};
+    b0[2] = F2{uc[0].x * wc[1].x - uc[1].x * wc[0].x, uc[0].y * wc[1].y - uc[1].y * wc[0].y};
+
+    // ---- omega2 of plane zc = zf - 1 (needs buf(zf), buf(zf - 2) own; buf(zf - 1) neighbours)
+    const int zc = zf - 1;
+    F2 q1[3];
+    {
+      const F2 bxu = sb_ld2(sr + 0 * FV::ARR + soff + FV::ROW), bxd = sb_ld2(sr + 0 * FV::ARR + soff - FV::ROW);
+      const F2 bzu = sb_ld2(sr + 1 * FV::ARR + soff + FV::ROW), bzd = sb_ld2(sr + 1 * FV::ARR + soff - FV::ROW);
+      // x neighbours of buf_y, buf_z at plane zc: inside the strip or from the adjacent lane
+      const float byl = __shfl_up_sync(0xffffffffu, b1[1].y, 1), byr = __shfl_down_sync(0xffffffffu, b1[1].x, 1);
+      const float bzl = __shfl_up_sync(0xffffffffu, b1[2].y, 1), bzr = __shfl_down_sync(0xffffffffu, b1[2].x, 1);
+      const int zmask = ((zc >= 1 && zc < g.mz - 1) ? 1 : 0) | ((zc >= zlo && zc < zhi) ? 2 : 0);
+      const bool wr0 = FAST ? (zmask & 2) != 0 : (m0 & zmask & 3) != 0;
+      const bool wr1 = FAST ? (zmask & 2) != 0 : (m1 & zmask & 3) != 0;
+      // curl_x = d(buf_z)/dy - d(buf_y)/dz ; curl_y = d(buf_x)/dz - d(buf_z)/dx ; curl_z = d(buf_y)/dx - d(buf_x)/dy
+      q1[0] = wp[0];
+      q1[1] = wp[1];
+      q1[2] = wp[2];
+      if (wr0) {
+        q1[0].x += p * (bzu.x - bzd.x - b0[1].x + b2xy[1].x);
+        q1[1].x += p * (b0[0].x - b2xy[0].x - b1[2].y + bzl);
+        q1[2].x += p * (b1[1].y - byl - bxu.x + bxd.x);
+      }
+      if (wr1) {
+        q1[0].y += p * (bzu.y - bzd.y - b0[1].y + b2xy[1].y);
+        q1[1].y += p * (b0[0].y - b2xy[0].y - bzr + b1[2].x);
+        q1[2].y += p * (byr - b1[1].x - bxu.y + bxd.y);
+      }
+    }
+    // ---- result of plane zo = zf - 2 (needs omega2(zf - 1), omega2(zf - 3) own; omega2(zf - 2) neighbours)
+    const int zo = zf - 2;
+    if (zo >= zb && zo < ze) {
+      const int zmask = ((zo >= 1 && zo < g.mz - 1) ? 1 : 0) | ((zo >= zlo && zo < zhi) ? 2 : 0);
+      const bool zring = zo < zring_lo || zo >= zring_hi;
+      const bool lap0 = (FAST ? (zmask & 2) != 0 : ((m0 & zmask & 3) != 0 && !(m0 & 8))) && !zring;
+      const bool lap1 = (FAST ? (zmask & 2) != 0 : ((m1 & zmask & 3) != 0 && !(m1 & 8))) && !zring;
+      F2 r[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const F2 qu = sb_ld2(sr + (2 + c) * FV::ARR + soff + FV::ROW);
+        const F2 qd = sb_ld2(sr + (2 + c) * FV::ARR + soff - FV::ROW);
+        const float ql = __shfl_up_sync(0xffffffffu, q2[c].y, 1), qr = __shfl_down_sync(0xffffffffu, q2[c].x, 1);
+        r[c] = q2[c];
+        if (lap0) {
+          const float s = q2[c].y + ql + qu.x + qd.x + q1[c].x + q3[c].x;
+          r[c].x += d * (s - 6.f * q2[c].x);
+        }
+        if (lap1) {
+          const float s = qr + q2[c].x + qu.y + qd.y + q1[c].y + q3[c].y;
+          r[c].y += d * (s - 6.f * q2[c].y);
+        }
+      }
+      if (st_row) {
+        const long long gi = (long long)zo * plane + goff;
+        if (FAST || pair) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sb_st2(out + gi + c * vol, r[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (in0) out[gi + c * vol] = r[c].x;
+            if (in1) out[gi + 1 + c * vol] = r[c].y;
+          }
+        }
+      }
+    } else {
+      // (the shuffles above are warp-collective: keep every lane on the same path) -- nothing to do
+    }
+    // ---- publish this iteration's planes for the y neighbours of the next one
+    sb_st2(sw + 0 * FV::ARR + soff, b0[0]);
+    sb_st2(sw + 1 * FV::ARR + soff, b0[2]);
+    sb_st2(sw + 2 * FV::ARR + soff, q1[0]);
+    sb_st2(sw + 3 * FV::ARR + soff, q1[1]);
+    sb_st2(sw + 4 * FV::ARR + soff, q1[2]);
+    __syncthreads();
+    // ---- shift the z history
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      q3[c] = q2[c];
+      q2[c] = q1[c];
+      wp[c] = wc[c];
+    }
+    b2xy[0] = b1[0];
+    b2xy[1] = b1[1];
+    b1[0] = b0[0];
+    b1[1] = b0[1];
+    b1[2] = b0[2];
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(32 * R)
+    sb_vorticity_fused_v2_kernel(SbGeom g, float* __restrict__ out, const float* __restrict__ w,
+                                 const float* __restrict__ u, float p, float d, int zchunk) {
+  using FV = FusedV2<R>;
+  SB_DYN_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  // the block's footprint: x in [x0 - 2, x0 + 62), y in [y0 - 2, y0 + R - 2); omega2 is evaluated on
+  // footprint - 1: FAST when that region lies where the reference's interior call writes (mask B, no ring)
+  const int x0 = (int)blockIdx.x * FV::TXU, y0 = (int)blockIdx.y * FV::TYU;
+  const bool fast = x0 - 1 >= g.gs + 1 && x0 + FV::TXU <= g.mx - g.gs - 2 && y0 - 1 >= g.gs + 1 &&
+                    y0 + FV::TYU <= g.my - g.gs - 2 && x0 + 62 <= g.mx && y0 + R - 2 <= g.my;
+  if (fast)
+    sb_vorticity_fused_v2_body<R, true>(g, out, w, u, p, d, zchunk, smem);
+  else
+    sb_vorticity_fused_v2_body<R, false>(g, out, w, u, p, d, zchunk, smem);
+}
+
+template <int R>
+static int launch_fused_v2(const SbGeom& g, void* out, const void* w, const void* u, double p, double d,
+                           void* stream) {
+  using FV = FusedV2<R>;
+  const size_t smem = sizeof(float) * FV::ELEMS;
+  const unsigned gx = (g.mx + FV::TXU - 1) / FV::TXU, gy = (g.my + FV::TYU - 1) / FV::TYU;
+  SB_KERNEL_ATTR_SMEM((sb_vorticity_fused_v2_kernel<R>), smem);
+  long long resident = 148;
+#ifndef SB200_EMU
+  {
+    static long long cached = 0;
+    if (cached == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_vorticity_fused_v2_kernel<R>, FV::NT, smem);
+      cached = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    }
+    resident = cached;
+  }
+#endif
+  int chunks = 1, zchunk = g.mz;
+  {
+    long long best = -1;
+    const long long tiles = (long long)gx * gy;
+    for (int c = 1; c <= g.mz; ++c) {
+      const int zc = (g.mz + c - 1) / c;
+      if (zc < 8 && c > 1) break;
+      const int cc = (g.mz + zc - 1) / zc;
+      const long long waves = (tiles * cc + resident - 1) / resident;
+      const long long cost = waves * (zc + 4);
+      if (best < 0 || cost < best) {
+        best = cost;
+        chunks = cc;
+        zchunk = zc;
+      }
+    }
+  }
+  SB_LAUNCH_COOP((sb_vorticity_fused_v2_kernel<R>), dim3(gx, gy, (unsigned)chunks), dim3(FV::NT), smem, stream, g,
+                 (float*)out, (const float*)w, (const float*)u, (float)p, (float)d, zchunk);
+  SB_CHECK_LAUNCH("vorticity_fused_v2");
+  return 0;
+}
+
 template <typename T, int TY, int TX, int NT>
 static int launch_fused(const SbGeom& g, void* out, const void* w, const void* u, double p, double d,
                         void* stream) {
@@ -264,7 +515,15 @@ extern "C" int sb200_vorticity_rhs_fused_3d(const sb200_grid_t* gr, void* out, c
   // 16 x 32 tiles, 256 threads: (20 x 36) and (18 x 34) staged cells fill 3 passes of the block almost
   // completely (94 % / 80 %) and the halo overhead is 1.41x; measured 262 us at 256^3 against 363 us
   // for 8 x 64 (and 278-417 us for 12x32, 24x32, 16x48, 16x16, 512 or 128 threads)
-  if (gr->dtype == SB200_F32)
+  if (gr->dtype == SB200_F32) {
+    // version 2 needs even row lengths (8-byte strips); SB200_FUSED_V2 = 0 / rows selects for measurements
+    static const int v2 = getenv("SB200_FUSED_V2") ? atoi(getenv("SB200_FUSED_V2")) : 24;
+    if (v2 > 0 && (g.mx & 1) == 0) {
+      if (v2 == 16) return launch_fused_v2<16>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+      if (v2 == 20) return launch_fused_v2<20>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+      return launch_fused_v2<24>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+    }
     return launch_fused<float, 16, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+  }
   return launch_fused<double, 8, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
 }

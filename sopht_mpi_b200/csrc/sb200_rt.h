@@ -103,6 +103,11 @@ static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
   return sb_emu_shfl(v, l + d < 32 ? l + d : l);
 }
 template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+  unsigned l = sbemu::t_linear_tid % 32;
+  return sb_emu_shfl(v, l >= d ? l - d : l);
+}
+template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src) { return sb_emu_shfl(v, (unsigned)src); }
 
 template <typename T>

@@ -150,54 +150,94 @@ struct UpdateVorticityOp {
 };
 
 // ---- forcing update for a forcing field that is zero almost everywhere (immersed-boundary forcing
-// lives within two cells of the Lagrangian points).  Same cells and arithmetic as UpdateVorticityOp,
-// but the read-modify-write of omega is skipped where curl(F) == 0 (omega + 0 == omega), and every
-// block records in `flags` whether its 256 cells hold a non-zero forcing value, so that the `F = 0`
-// that ends the step (flow_simulators_mpi_3d.py:422-424) only has to touch those blocks
-// (sb200_clear_flagged_tiles).  Block (blockIdx.x, z) <-> flag z * gridDim.x + blockIdx.x.
+// lives within two cells of the Lagrangian points).  The padded array is cut into flat chunks of 1024
+// consecutive cells.  Pass 1 reads F once (vectorised, the only dense traffic: 3 W per cell) and flags
+// the chunks that hold a non-zero value; pass 2 applies UpdateVorticityOp's arithmetic to the chunks
+// whose stencil neighbourhood (x +- 1, y +- 1, z +- 1) touches a flagged chunk and skips the others
+// (omega + prefactor * curl(0) == omega); sb200_clear_flagged_tiles zeroes the flagged chunks only, which
+// is the `F = 0` that ends the step (flow_simulators_mpi_3d.py:422-424).  Exact for any F.
+#define SB_CHUNK 1024
 template <typename T>
 __global__ void __launch_bounds__(256)
-    sb_update_vorticity_sparse_kernel(SbGeom g, T* __restrict__ w, const T* __restrict__ f, T p,
-                                      unsigned char* flags) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int z = blockIdx.y;
-  if (idx >= g.plane) return;
-  const int y = (int)(idx / g.mx);
-  const int x = (int)(idx - (long long)y * g.mx);
-  const long long i = (long long)z * g.plane + idx;
-  bool nonzero = f[i] != T(0) || f[i + g.vol] != T(0);
-  if (g.dim == 3) nonzero = nonzero || f[i + 2 * g.vol] != T(0);
-  if (nonzero) flags[(long long)blockIdx.y * gridDim.x + blockIdx.x] = 1;  // (every writer stores 1)
-  if (!g.deep(z, y, x) && !g.written(z, y, x, 1)) return;
-  if (g.dim == 3) {
-    T cx, cy, cz;
-    curl3_at(g, f, i, p, cx, cy, cz);
-    if (cx != T(0)) w[i] += cx;
-    if (cy != T(0)) w[i + g.vol] += cy;
-    if (cz != T(0)) w[i + 2 * g.vol] += cz;
-  } else {
-    const T* fx = f;
-    const T* fy = f + g.vol;
-    const T c = p * (fy[i + 1] - fy[i - 1] - fx[i + g.mx] + fx[i - g.mx]);
-    if (c != T(0)) w[i] += c;
+    sb_flag_nonzero_chunks_kernel(const T* __restrict__ f, int ncomp, long long vol, long long nchunks,
+                                  unsigned char* flags) {
+  const bool vec = (vol & 3) == 0;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const long long i = c * SB_CHUNK + 4 * (long long)threadIdx.x;
+    bool nz = false;
+    if (vec && i + 3 < vol) {
+      for (int k = 0; k < ncomp; ++k) {
+        const T* q = f + k * vol + i;
+        if constexpr (sizeof(T) == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(q);
+          nz = nz || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
+        } else {
+          nz = nz || q[0] != T(0) || q[1] != T(0) || q[2] != T(0) || q[3] != T(0);
+        }
+      }
+    } else {
+      for (int k = 0; k < ncomp; ++k)
+        for (int e = 0; e < 4; ++e)
+          if (i + e < vol) nz = nz || f[k * vol + i + e] != T(0);
+    }
+    if (nz) flags[c] = 1;  // (every writer stores 1)
+  }
+}
+// does the stencil of any cell of chunk c read a flagged chunk?
+SB_D bool sb_chunk_active(const unsigned char* __restrict__ flags, long long c, long long nchunks, const SbGeom& g) {
+  const long long lo = c * SB_CHUNK, hi = lo + SB_CHUNK - 1;
+  const long long offs[3] = {1, (long long)g.mx, g.plane};
+  bool on = flags[c] != 0;
+  const int noff = g.dim == 3 ? 3 : 2;
+  for (int k = 0; k < noff; ++k) {
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      const long long a = lo + sgn * offs[k], b = hi + sgn * offs[k];
+      for (long long q = (a < 0 ? 0 : a / SB_CHUNK); q <= b / SB_CHUNK && q < nchunks; ++q)
+        if (b >= 0) on = on || flags[q] != 0;
+    }
+  }
+  return on;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sb_update_vorticity_flagged_kernel(SbGeom g, T* __restrict__ w, const T* __restrict__ f, T p, long long nchunks,
+                                       const unsigned char* __restrict__ flags) {
+  const UpdateVorticityOp<T> op{w, f, p};
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    if (!sb_chunk_active(flags, c, nchunks, g)) continue;
+    for (int e = 0; e < 4; ++e) {
+      const long long i = c * SB_CHUNK + e * 256 + threadIdx.x;
+      if (i >= g.vol) continue;
+      const int z = (int)(i / g.plane);
+      const long long r = i - (long long)z * g.plane;
+      const int y = (int)(r / g.mx), x = (int)(r - (long long)y * g.mx);
+      op(g, z, y, x);
+    }
   }
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
-    sb_clear_flagged_kernel(SbGeom g, T* __restrict__ f, int ncomp, const unsigned char* __restrict__ flags) {
-  if (!flags[(long long)blockIdx.y * gridDim.x + blockIdx.x]) return;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= g.plane) return;
-  const long long i = (long long)blockIdx.y * g.plane + idx;
-  for (int c = 0; c < ncomp; ++c) f[i + c * g.vol] = T(0);
+    sb_clear_flagged_kernel(T* __restrict__ f, int ncomp, long long vol, long long nchunks,
+                            const unsigned char* __restrict__ flags) {
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    if (!flags[c]) continue;
+    for (int e = 0; e < 4; ++e) {
+      const long long i = c * SB_CHUNK + e * 256 + threadIdx.x;
+      if (i < vol)
+        for (int k = 0; k < ncomp; ++k) f[k * vol + i] = T(0);
+    }
+  }
 }
-static inline dim3 sb_tile_grid(const SbGeom& g) { return dim3((unsigned)((g.plane + 255) / 256), (unsigned)g.mz); }
+static inline long long sb_chunk_count(const SbGeom& g) { return (g.vol + SB_CHUNK - 1) / SB_CHUNK; }
+static inline unsigned sb_chunk_grid(long long nchunks) {
+  const long long cap = 148LL * 16;
+  return (unsigned)(nchunks < cap ? nchunks : cap);
+}
 
 extern "C" int64_t sb200_tile_flag_count(const sb200_grid_t* gr) {
   SbGeom g;
   if (sb_make_geom(gr, &g) != 0) return 0;
-  const dim3 grid = sb_tile_grid(g);
-  return (int64_t)grid.x * grid.y;
+  return (int64_t)sb_chunk_count(g);
 }
 extern "C" int sb200_update_vorticity_from_sparse_forcing(const sb200_grid_t* gr, void* vorticity,
                                                           const void* velocity_forcing, double prefactor,
@@ -205,11 +245,18 @@ extern "C" int sb200_update_vorticity_from_sparse_forcing(const sb200_grid_t* gr
   SbGeom g;
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
   SB_REQUIRE(vorticity && velocity_forcing && tile_flags, "update_vorticity_from_sparse_forcing: null pointer");
+  const long long nchunks = sb_chunk_count(g);
+  const unsigned grid = sb_chunk_grid(nchunks);
   SB_DISPATCH_DTYPE(gr->dtype, {
-    SB_LAUNCH(sb_update_vorticity_sparse_kernel<T>, sb_tile_grid(g), dim3(256), 0, stream, g, (T*)vorticity,
-              (const T*)velocity_forcing, (T)prefactor, (unsigned char*)tile_flags);
+    SB_LAUNCH(sb_flag_nonzero_chunks_kernel<T>, dim3(grid), dim3(256), 0, stream, (const T*)velocity_forcing,
+              g.dim, g.vol, nchunks, (unsigned char*)tile_flags);
   });
-  SB_CHECK_LAUNCH("update_vorticity_sparse");
+  SB_CHECK_LAUNCH("flag_nonzero_chunks");
+  SB_DISPATCH_DTYPE(gr->dtype, {
+    SB_LAUNCH(sb_update_vorticity_flagged_kernel<T>, dim3(grid), dim3(256), 0, stream, g, (T*)vorticity,
+              (const T*)velocity_forcing, (T)prefactor, nchunks, (const unsigned char*)tile_flags);
+  });
+  SB_CHECK_LAUNCH("update_vorticity_flagged");
   return 0;
 }
 extern "C" int sb200_clear_flagged_tiles(const sb200_grid_t* gr, void* field, int ncomp, void* tile_flags,
@@ -217,13 +264,13 @@ extern "C" int sb200_clear_flagged_tiles(const sb200_grid_t* gr, void* field, in
   SbGeom g;
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
   SB_REQUIRE(field && tile_flags && ncomp >= 1 && ncomp <= 3, "clear_flagged_tiles: bad arguments");
+  const long long nchunks = sb_chunk_count(g);
   SB_DISPATCH_DTYPE(gr->dtype, {
-    SB_LAUNCH(sb_clear_flagged_kernel<T>, sb_tile_grid(g), dim3(256), 0, stream, g, (T*)field, ncomp,
-              (const unsigned char*)tile_flags);
+    SB_LAUNCH(sb_clear_flagged_kernel<T>, dim3(sb_chunk_grid(nchunks)), dim3(256), 0, stream, (T*)field, ncomp,
+              g.vol, nchunks, (const unsigned char*)tile_flags);
   });
   SB_CHECK_LAUNCH("clear_flagged_tiles");
-  const dim3 grid = sb_tile_grid(g);
-  const int e = sb_memset_async(tile_flags, 0, (size_t)grid.x * grid.y, stream);
+  const int e = sb_memset_async(tile_flags, 0, (size_t)nchunks, stream);
   if (e) {
     sb_set_error("memset: %s", sb_error_string(e));
     return -2;

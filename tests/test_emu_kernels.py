@@ -430,7 +430,7 @@ def test_pruned_fft_poisson_pipeline_2d(real_t):
 
 
 @pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
-@pytest.mark.parametrize("n", [(20, 24, 70), (9, 17, 66)], ids=["a", "b"])
+@pytest.mark.parametrize("n", [(20, 24, 70), (9, 17, 66), (6, 60, 200)], ids=["a", "b", "interior-blocks"])
 def test_fused_vorticity_update_equals_the_three_reference_sweeps(real_t, n):
     """csrc/fused.cu against cross product -> curl update -> diffusion composed from the
     oracle's restatement of the reference wrappers (bit-for-bit the same cells)."""
@@ -547,7 +547,7 @@ def test_sparse_forcing_update_and_flagged_reset(dim, sparse):
     real_t = np.float32
     rng = np.random.default_rng(12)
     gs = 2
-    n = (10, 37, 45) if dim == 3 else (37, 45)
+    n = (10, 37, 45) if dim == 3 else (150, 200)
     shape = tuple(v + 2 * gs for v in n)
     g = _lib.make_grid(dim, real_t, gs, n, [1] * (2 * dim))
     w = rng.uniform(size=((3,) + shape) if dim == 3 else shape).astype(real_t)

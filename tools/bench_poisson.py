@@ -38,6 +38,15 @@ def main():
         ms = a.elapsed_time(b) / reps
         gbs = 86 * 4 * n ** 3 / (ms * 1e-3) / 1e9
         line = f"n={n} backend={solver.backend} {ms:.3f} ms/vector-solve  {gbs:.0f} GB/s algorithmic (86 W/cell)"
+        if solver.backend == "fft":
+            solver.set_profiling(True)
+            acc = {}
+            for _ in range(reps):
+                solver.vector_field_solve(solution_vector_field=s, rhs_vector_field=r)
+                for k, v in solver.last_stage_ms().items():
+                    acc[k] = acc.get(k, 0.0) + v / reps
+            solver.set_profiling(False)
+            line += "  stages[ms]: " + " ".join(f"{v:.3f}" for v in acc.values())
         if check:
             ref = UnboundedPoissonSolverMPI3D(n, n, n, mpi_construct=mc, ghost_size=gs, x_range=1.0,
                                               real_t=np.float32, backend="cufft")
