@@ -64,7 +64,8 @@ int sb200_update_vorticity_from_velocity_forcing(const sb200_grid_t* g, void* vo
                                                  const void* velocity_forcing, double prefactor, void* stream);
 /* The same update for a forcing field that is zero almost everywhere (immersed-boundary forcing):
  * F is read once to flag the 1024-cell chunks of the padded array that hold a non-zero value
- * (`tile_flags`: device bytes, sb200_tile_flag_count(g) of them, zero-initialised once by the caller),
+ * (`tile_flags`: a device work buffer of sb200_tile_flag_count(g) BYTES, zero-initialised once by the
+ * caller: per-chunk flags and the compact lists of flagged / active chunks),
  * omega is only touched on chunks whose stencil reaches a flagged chunk.  sb200_clear_flagged_tiles
  * zeroes `field` on the flagged chunks and clears the flags: the `set_field(F, 0)` that ends the reference step
  * (simulator/flow/flow_simulators_mpi_3d.py:422-424, flow_simulators_mpi_2d.py:291-293) at a cost
@@ -185,6 +186,11 @@ int sb200_enable_peer_access(int device, int peer_device);
 int sb200_peer_copy(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream);
 int sb200_peer_copy_blocks(int n, void* const* dst, const int* dst_device, const void* const* src,
                            int src_device, int64_t bytes, void* stream);
+/* The exchange as one kernel: block k (bytes, a multiple of 16) is copied from src[k] (local) to dst[k] (an
+ * IPC-mapped pointer into rank k's buffer, or a local pointer) by blocks_per_peer thread blocks of
+ * 512 threads each (<= 0: default), all n <= 8 destinations concurrently over NVLink. */
+int sb200_peer_push_blocks(int n, void* const* dst, const void* const* src, int64_t bytes, int blocks_per_peer,
+                           void* stream);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

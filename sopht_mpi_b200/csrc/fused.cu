@@ -263,41 +263,52 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
   for (int i = threadIdx.x; i < FV::ELEMS; i += FV::NT) smem[i] = 0.f;
   __syncthreads();
 
-  for (int zf = zb - 2; zf <= ze + 1; ++zf) {
-    const int par = zf & 1;
-    float* sw = sA + par * 5 * FV::ARR;               // written this iteration
-    const float* sr = sA + (par ^ 1) * 5 * FV::ARR;   // written by the previous iteration
-    // ---- plane zf: omega, u -> u x omega
-    F2 wc[3], uc[3];
-    const bool zin = zf >= 0 && zf < g.mz;
+  auto load_plane = [&](int z, F2 (&wl)[3], F2 (&ul)[3]) {
+    const bool zin = z >= 0 && z < g.mz;
     if (zin && (FAST || pair)) {
-      const long long gi = (long long)zf * plane + goff;
+      const long long gi = (long long)z * plane + goff;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        wc[c] = sb_ld2(w + gi + c * vol);
-        uc[c] = sb_ld2(u + gi + c * vol);
+        wl[c] = sb_ld2(w + gi + c * vol);
+        ul[c] = sb_ld2(u + gi + c * vol);
       }
     } else {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        wc[c] = F2{0.f, 0.f};
-        uc[c] = F2{0.f, 0.f};
+        wl[c] = F2{0.f, 0.f};
+        ul[c] = F2{0.f, 0.f};
       }
       if (!FAST && zin) {
-        const long long gi = (long long)zf * plane + goff;
+        const long long gi = (long long)z * plane + goff;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           if (in0) {
-            wc[c].x = w[gi + c * vol];
-            uc[c].x = u[gi + c * vol];
+            wl[c].x = w[gi + c * vol];
+            ul[c].x = u[gi + c * vol];
           }
           if (in1) {
-            wc[c].y = w[gi + 1 + c * vol];
-            uc[c].y = u[gi + 1 + c * vol];
+            wl[c].y = w[gi + 1 + c * vol];
+            ul[c].y = u[gi + 1 + c * vol];
           }
         }
       }
     }
+  };
+  F2 wn[3], un[3];
+  load_plane(zb - 2, wn, un);
+
+  for (int zf = zb - 2; zf <= ze + 1; ++zf) {
+    const int par = zf & 1;
+    float* sw = sA + par * 5 * FV::ARR;               // written this iteration
+    const float* sr = sA + (par ^ 1) * 5 * FV::ARR;   // written by the previous iteration
+    // ---- plane zf: omega, u (loaded one iteration ahead) -> u x omega; start the loads of plane zf + 1
+    F2 wc[3], uc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      wc[c] = wn[c];
+      uc[c] = un[c];
+    }
+    if (zf + 1 <= ze + 1) load_plane(zf + 1, wn, un);
     F2 b0[3];
     b0[0] = F2{uc[1].x * wc[2].x - uc[2].x * wc[1].x, uc[1].y * wc[2].y - uc[2].y * wc[1].y};
     b0[1] = F2{uc[2].x * wc[0].x - uc[0].x * wc[2].x, uc[2].y * wc[0].y - uc[0].y * wc[2].y};

@@ -952,7 +952,7 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
     const int inner = p->nranks > 1 ? st->kxl : nx + 1;
     st->ng = (inner + 7) / 8;
     static const bool env_off = getenv("SB200_ZCONV") && atoi(getenv("SB200_ZCONV")) == 0;
-    st->zconv = !env_off && sizeof(T) == 4 && p->dim == 3 && p->nranks == 1 && (st->pz.log2n == 9 || st->pz.log2n == 10) &&
+    st->zconv = !env_off && sizeof(T) == 4 && p->dim == 3 && (st->pz.log2n == 9 || st->pz.log2n == 10) &&
                 sb_use_p32(1, st->pz.log2n);
   }
   const size_t b_bytes = p->dim != 3 ? 0
@@ -1200,6 +1200,18 @@ static int slab_spectral_t(sb200_poisson* p, void* recv, int ncomp, void* stream
   const SbSlabPlan<T> sp = slab_plan<T>(p, st, ncomp);
   SbGreensTable<T> none{nullptr, 0, 0};
   int e;
+  if (st->zconv) {
+    // tile-contiguous B (see fft_solve_t): Bt[c][kx group][ky][z][8]; the padding lines of the last group
+    // stay zero
+    const long long NKY = 2LL * p->ny, tile = (long long)p->nz * 8;
+    SbLines lb{sp.kxl, p->nz, ncomp, 8, (long long)st->ng * NKY * tile, tile};
+    lb.gsh = 3;
+    lb.s_grp = NKY * tile;
+    if ((e = launch_strided<T, 0>(st->py, (const C2<T>*)recv, sp.lr, st->B, lb, st->twy, none, stream))) return e;
+    if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * p->ny, stream)))
+      return e;
+    return launch_strided<T, 2>(st->py, st->B, lb, (C2<T>*)recv, sp.lr, st->twy, none, stream);
+  }
   if ((e = launch_strided<T, 0>(st->py, (const C2<T>*)recv, sp.lr, st->B, sp.lbuf, st->twy, none, stream))) return e;
   SbGreensTable<T> gt{st->G, (long long)(p->ny + 1) * st->P, st->P, 2 * p->ny, 0};
   gt.g2 = st->G2;

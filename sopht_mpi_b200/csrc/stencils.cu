@@ -157,10 +157,17 @@ struct UpdateVorticityOp {
 // (omega + prefactor * curl(0) == omega); sb200_clear_flagged_tiles zeroes the flagged chunks only, which
 // is the `F = 0` that ends the step (flow_simulators_mpi_3d.py:422-424).  Exact for any F.
 #define SB_CHUNK 1024
+// work buffer (ints): flags[n] | active[n] | list of flagged chunks [n] | list of active chunks [n] | 2 counters
+struct SbChunkBuf {
+  int *flags, *active, *nz_list, *act_list, *count;
+};
+static inline SbChunkBuf sb_chunk_buf(void* p, long long n) {
+  int* b = (int*)p;
+  return SbChunkBuf{b, b + n, b + 2 * n, b + 3 * n, b + 4 * n};
+}
 template <typename T>
 __global__ void __launch_bounds__(256)
-    sb_flag_nonzero_chunks_kernel(const T* __restrict__ f, int ncomp, long long vol, long long nchunks,
-                                  unsigned char* flags) {
+    sb_flag_nonzero_chunks_kernel(const T* __restrict__ f, int ncomp, long long vol, long long nchunks, SbChunkBuf b) {
   const bool vec = (vol & 3) == 0;
   for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const long long i = c * SB_CHUNK + 4 * (long long)threadIdx.x;
@@ -180,31 +187,34 @@ __global__ void __launch_bounds__(256)
         for (int e = 0; e < 4; ++e)
           if (i + e < vol) nz = nz || f[k * vol + i + e] != T(0);
     }
-    if (nz) flags[c] = 1;  // (every writer stores 1)
+    // the first thread to flag a chunk appends it to the list
+    if (nz && atomicAdd(&b.flags[c], 1) == 0) b.nz_list[atomicAdd(&b.count[0], 1)] = (int)c;
   }
 }
-// does the stencil of any cell of chunk c read a flagged chunk?
-SB_D bool sb_chunk_active(const unsigned char* __restrict__ flags, long long c, long long nchunks, const SbGeom& g) {
-  const long long lo = c * SB_CHUNK, hi = lo + SB_CHUNK - 1;
+// every chunk whose stencil (x +- 1, y +- 1, z +- 1) reads a flagged chunk becomes active
+__global__ void __launch_bounds__(256) sb_dilate_chunks_kernel(SbGeom g, long long nchunks, SbChunkBuf b) {
+  const int n = b.count[0];
   const long long offs[3] = {1, (long long)g.mx, g.plane};
-  bool on = flags[c] != 0;
   const int noff = g.dim == 3 ? 3 : 2;
-  for (int k = 0; k < noff; ++k) {
-    for (int sgn = -1; sgn <= 1; sgn += 2) {
-      const long long a = lo + sgn * offs[k], b = hi + sgn * offs[k];
-      for (long long q = (a < 0 ? 0 : a / SB_CHUNK); q <= b / SB_CHUNK && q < nchunks; ++q)
-        if (b >= 0) on = on || flags[q] != 0;
-    }
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const long long c = b.nz_list[k], lo = c * SB_CHUNK, hi = lo + SB_CHUNK - 1;
+    if (atomicAdd(&b.active[c], 1) == 0) b.act_list[atomicAdd(&b.count[1], 1)] = (int)c;
+    for (int o = 0; o < noff; ++o)
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const long long a = lo + sgn * offs[o], e = hi + sgn * offs[o];
+        if (e < 0) continue;
+        for (long long q = (a < 0 ? 0 : a / SB_CHUNK); q <= e / SB_CHUNK && q < nchunks; ++q)
+          if (atomicAdd(&b.active[q], 1) == 0) b.act_list[atomicAdd(&b.count[1], 1)] = (int)q;
+      }
   }
-  return on;
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
-    sb_update_vorticity_flagged_kernel(SbGeom g, T* __restrict__ w, const T* __restrict__ f, T p, long long nchunks,
-                                       const unsigned char* __restrict__ flags) {
+    sb_update_vorticity_flagged_kernel(SbGeom g, T* __restrict__ w, const T* __restrict__ f, T p, SbChunkBuf b) {
   const UpdateVorticityOp<T> op{w, f, p};
-  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    if (!sb_chunk_active(flags, c, nchunks, g)) continue;
+  const int n = b.count[1];
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    const long long c = b.act_list[k];
     for (int e = 0; e < 4; ++e) {
       const long long i = c * SB_CHUNK + e * 256 + threadIdx.x;
       if (i >= g.vol) continue;
@@ -217,14 +227,14 @@ __global__ void __launch_bounds__(256)
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
-    sb_clear_flagged_kernel(T* __restrict__ f, int ncomp, long long vol, long long nchunks,
-                            const unsigned char* __restrict__ flags) {
-  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    if (!flags[c]) continue;
+    sb_clear_flagged_kernel(T* __restrict__ f, int ncomp, long long vol, SbChunkBuf b) {
+  const int n = b.count[0];
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    const long long c = b.nz_list[k];
     for (int e = 0; e < 4; ++e) {
       const long long i = c * SB_CHUNK + e * 256 + threadIdx.x;
       if (i < vol)
-        for (int k = 0; k < ncomp; ++k) f[k * vol + i] = T(0);
+        for (int q = 0; q < ncomp; ++q) f[q * vol + i] = T(0);
     }
   }
 }
@@ -233,11 +243,12 @@ static inline unsigned sb_chunk_grid(long long nchunks) {
   const long long cap = 148LL * 16;
   return (unsigned)(nchunks < cap ? nchunks : cap);
 }
+static inline size_t sb_chunk_buf_bytes(long long nchunks) { return sizeof(int) * (size_t)(4 * nchunks + 4); }
 
 extern "C" int64_t sb200_tile_flag_count(const sb200_grid_t* gr) {
   SbGeom g;
   if (sb_make_geom(gr, &g) != 0) return 0;
-  return (int64_t)sb_chunk_count(g);
+  return (int64_t)sb_chunk_buf_bytes(sb_chunk_count(g));
 }
 extern "C" int sb200_update_vorticity_from_sparse_forcing(const sb200_grid_t* gr, void* vorticity,
                                                           const void* velocity_forcing, double prefactor,
@@ -245,16 +256,20 @@ extern "C" int sb200_update_vorticity_from_sparse_forcing(const sb200_grid_t* gr
   SbGeom g;
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
   SB_REQUIRE(vorticity && velocity_forcing && tile_flags, "update_vorticity_from_sparse_forcing: null pointer");
+  SB_REQUIRE(g.vol / SB_CHUNK < (1LL << 30), "update_vorticity_from_sparse_forcing: field too large");
   const long long nchunks = sb_chunk_count(g);
+  const SbChunkBuf b = sb_chunk_buf(tile_flags, nchunks);
   const unsigned grid = sb_chunk_grid(nchunks);
   SB_DISPATCH_DTYPE(gr->dtype, {
     SB_LAUNCH(sb_flag_nonzero_chunks_kernel<T>, dim3(grid), dim3(256), 0, stream, (const T*)velocity_forcing,
-              g.dim, g.vol, nchunks, (unsigned char*)tile_flags);
+              g.dim, g.vol, nchunks, b);
   });
   SB_CHECK_LAUNCH("flag_nonzero_chunks");
+  SB_LAUNCH(sb_dilate_chunks_kernel, dim3(148), dim3(256), 0, stream, g, nchunks, b);
+  SB_CHECK_LAUNCH("dilate_chunks");
   SB_DISPATCH_DTYPE(gr->dtype, {
     SB_LAUNCH(sb_update_vorticity_flagged_kernel<T>, dim3(grid), dim3(256), 0, stream, g, (T*)vorticity,
-              (const T*)velocity_forcing, (T)prefactor, nchunks, (const unsigned char*)tile_flags);
+              (const T*)velocity_forcing, (T)prefactor, b);
   });
   SB_CHECK_LAUNCH("update_vorticity_flagged");
   return 0;
@@ -265,12 +280,13 @@ extern "C" int sb200_clear_flagged_tiles(const sb200_grid_t* gr, void* field, in
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
   SB_REQUIRE(field && tile_flags && ncomp >= 1 && ncomp <= 3, "clear_flagged_tiles: bad arguments");
   const long long nchunks = sb_chunk_count(g);
+  const SbChunkBuf b = sb_chunk_buf(tile_flags, nchunks);
   SB_DISPATCH_DTYPE(gr->dtype, {
     SB_LAUNCH(sb_clear_flagged_kernel<T>, dim3(sb_chunk_grid(nchunks)), dim3(256), 0, stream, (T*)field, ncomp,
-              g.vol, nchunks, (const unsigned char*)tile_flags);
+              g.vol, b);
   });
   SB_CHECK_LAUNCH("clear_flagged_tiles");
-  const int e = sb_memset_async(tile_flags, 0, (size_t)nchunks, stream);
+  const int e = sb_memset_async(tile_flags, 0, sb_chunk_buf_bytes(nchunks), stream);
   if (e) {
     sb_set_error("memset: %s", sb_error_string(e));
     return -2;

@@ -1,14 +1,17 @@
 """All-to-all of equal blocks over NVLink peer memory (one process per GPU, one node).
 
 Every rank allocates its exchange buffers, publishes them through CUDA IPC and maps the buffers of
-all other ranks; an exchange is then one device-to-device peer copy per destination, written
-straight into the destination rank's buffer by the copy engines (no SMs, unlike NCCL's send/recv
-kernels, which compete with the transform kernels the exchange is overlapped with), followed by a
-tiny NCCL all-reduce that orders "all blocks have landed" on every rank's stream.  Replaces the MPI
-``Alltoallw`` inside mpi4py-fft's transposes (reference ``poisson_solver_3d/fft_mpi_3d.py:27-48``).
+all other ranks; an exchange is then ONE small kernel (``sb200_peer_push_blocks``) whose thread blocks
+store every destination block straight into the destination rank's buffer, all peers concurrently
+through the NVSwitch, followed by a tiny NCCL all-reduce that orders "all blocks have landed" on
+every rank's stream.  Replaces the MPI ``Alltoallw`` inside mpi4py-fft's transposes (reference
+``poisson_solver_3d/fft_mpi_3d.py:27-48``).
 
-If CUDA IPC is not available (different nodes, no peer access) the exchange falls back to NCCL.
+``SB200_EXCHANGE`` selects the transport for measurements: ``push`` (default), ``copy`` (one
+``cudaMemcpyPeerAsync`` per destination on the stream, round 1), ``nccl`` (all-to-all).  If CUDA IPC is
+not available (different nodes, no peer access) the exchange falls back to NCCL.
 """
+import os
 import ctypes
 
 import torch
@@ -29,6 +32,10 @@ class PeerExchange:
         self.peer = None
         self._plans = {}
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.transport = os.environ.get("SB200_EXCHANGE", "push")
+        self.blocks_per_peer = int(os.environ.get("SB200_PUSH_BLOCKS", "0"))
+        if self.transport == "nccl":
+            use_peer_copies = False
         if use_peer_copies and nranks > 1:
             try:
                 self._map_peers()
@@ -56,16 +63,19 @@ class PeerExchange:
         self._lib = _lib.load()
         self._dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._peer_dev = [self.peer[q][0].device.index for q in range(self.nranks)]
-        for q in range(self.nranks):
-            if q != self.rank:
-                # both directions: without the reverse mapping the driver stages the copy through
-                # the host (25 GB/s instead of ~640 GB/s, profiles/r01_peer_copy.txt)
-                _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._dev, self._peer_dev[q]))
-                _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._peer_dev[q], self._dev))
+        if self.transport == "copy":
+            for q in range(self.nranks):
+                if q != self.rank:
+                    # both directions: without the reverse mapping the driver stages the copy through
+                    # the host (25 GB/s instead of ~640 GB/s, profiles/r01_peer_copy.txt)
+                    _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._dev, self._peer_dev[q]))
+                    _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._peer_dev[q], self._dev))
 
     @property
     def mode(self):
-        return "cuda-ipc peer copies" if self.peer is not None else "nccl send/recv"
+        if self.peer is None:
+            return "nccl all-to-all"
+        return "cuda-ipc push kernel" if self.transport != "copy" else "cuda-ipc peer copies"
 
     def exchange(self, dst, src):
         """Block q of this rank's buffer `src` -> block `rank` of rank q's buffer `dst`, for every q
@@ -88,7 +98,11 @@ class PeerExchange:
             sptr = (ctypes.c_void_p * nranks)(*[s_blocks[q].data_ptr() for q in order])
             plan = self._plans[(dst, src)] = (dptr, ddev, sptr, s_blocks[0].numel() * 4)
         dptr, ddev, sptr, nbytes = plan
-        _lib.check(self._lib, self._lib.sb200_peer_copy_blocks(nranks, dptr, ddev, sptr, self._dev, nbytes, stream))
+        if self.transport == "copy":
+            _lib.check(self._lib, self._lib.sb200_peer_copy_blocks(nranks, dptr, ddev, sptr, self._dev, nbytes, stream))
+        else:
+            _lib.check(self._lib, self._lib.sb200_peer_push_blocks(nranks, dptr, sptr, nbytes, self.blocks_per_peer,
+                                                                  stream))
         # all ranks' copies precede their all-reduce in stream order: past this point every block of
         # `dst` has landed here, and every rank has finished reading the `src` blocks it was sent
         dist.all_reduce(self._flag)

@@ -562,9 +562,14 @@ def test_sparse_forcing_update_and_flagged_reset(dim, sparse):
     from emu_util import emu
 
     count = int(emu().sb200_tile_flag_count(ctypes.byref(g)))
-    flags = np.zeros(count, np.uint8)
-    call("sb200_update_vorticity_from_sparse_forcing", ctypes.byref(g), ptr(got), ptr(f), 0.37, ptr(flags), None)
+    work = np.zeros(count, np.uint8)
+    call("sb200_update_vorticity_from_sparse_forcing", ctypes.byref(g), ptr(got), ptr(f), 0.37, ptr(work), None)
     assert np.array_equal(got, ref)
-    assert 0 < flags.sum() and (flags.sum() < count if sparse else flags.sum() == count)
-    call("sb200_clear_flagged_tiles", ctypes.byref(g), ptr(f), dim, ptr(flags), None)
-    assert not f.any() and not flags.any()
+    ints = work.view(np.int32)
+    nchunks = (ints.size - 4) // 4
+    n_flagged, n_active = int(ints[4 * nchunks]), int(ints[4 * nchunks + 1])
+    assert n_flagged == int((ints[:nchunks] > 0).sum()) > 0
+    assert n_active == int((ints[nchunks:2 * nchunks] > 0).sum()) >= n_flagged
+    assert (n_active < nchunks) if sparse else (n_flagged == nchunks)
+    call("sb200_clear_flagged_tiles", ctypes.byref(g), ptr(f), dim, ptr(work), None)
+    assert not f.any() and not work.any()
