@@ -408,7 +408,7 @@ def main():
             eul_grid_velocity_field=sim.velocity_field, virtual_boundary_stiffness_coeff=w["k"],
             virtual_boundary_damping_coeff=w["c"], dx=sim.dx, grid_dim=3,
             forcing_grid_cls=lambda grid_dim, rigid_body: PrescribedForcingGrid(
-                grid_dim, pts, velocity_field=w["lag_vel"], max_lag_grid_dx=w["dx"]))
+                grid_dim, pts, velocity_field=w["lag_vel"], max_lag_grid_dx=w["dx"], static=True))
 
     cells = float(np.prod(grid))
 
@@ -575,18 +575,21 @@ def main():
 
         def e2e_api(i):
             fg.position_field[...] = pos_a if i % 2 else pos_b
+            fg.mark_moved()
             one_step()
             sink[...] = np.asarray(interactor.global_lag_grid_forcing_field).sum(axis=1)  # host read of the forces
             sink[0] += sim.get_max_vorticity()
 
         lag_bytes = fg.position_field.nbytes
-        e2e = {"value": measure(e2e_api), "unit": UNIT, "h2d_bytes_per_step": 2 * lag_bytes * (substeps + 1),
+        e2e = {"value": measure(e2e_api), "unit": UNIT, "h2d_bytes_per_step": 2 * lag_bytes,
                "d2h_bytes_per_step": lag_bytes * (substeps + 1) + 16,
-               "what": "public API, host buffers: Lagrangian positions + velocities (host numpy) uploaded for "
-                       "every interaction, Lagrangian forces + dt + max vorticity read back on the host, every step",
+               "what": "public API, host buffers: the body moves every step, so its Lagrangian positions + "
+                       "velocities (host numpy) are staged and uploaded every step; Lagrangian forces (every "
+                       "interaction), dt and max vorticity are read back on the host",
                "full_field_io_value": measure(e2e_fields),
                "full_field_io_bytes_per_step": {"h2d": field_bytes, "d2h": 2 * field_bytes}}
         fg.position_field[...] = pos_a
+        fg.mark_moved()
     else:
         e2e = {"value": measure(e2e_fields), "unit": UNIT, "h2d_bytes_per_step": field_bytes,
                "d2h_bytes_per_step": 2 * field_bytes,

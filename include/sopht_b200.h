@@ -188,9 +188,15 @@ int sb200_peer_copy_blocks(int n, void* const* dst, const int* dst_device, const
                            int src_device, int64_t bytes, void* stream);
 /* The exchange as one kernel: block k (bytes, a multiple of 16) is copied from src[k] (local) to dst[k] (an
  * IPC-mapped pointer into rank k's buffer, or a local pointer) by blocks_per_peer thread blocks of
- * 512 threads each (<= 0: default), all n <= 8 destinations concurrently over NVLink. */
+ * 512 threads each (<= 0: default), all n <= 8 destinations concurrently over NVLink.  With
+ * signal_flags != NULL, signal_flags[k] (an int32 in rank k's memory, IPC-mapped) is set to `epoch` once
+ * block k has landed completely (done_counters: n zero-initialised device int32 of the caller);
+ * sb200_peer_wait_flags makes the stream wait until the n flags of the local buffer have reached
+ * `epoch` (bounded spin: *error_flag, a device int32, is raised after ~2 s).  Together they replace the
+ * collective barrier behind the MPI Alltoallw of mpi4py-fft (poisson_solver_3d/fft_mpi_3d.py:27-48). */
 int sb200_peer_push_blocks(int n, void* const* dst, const void* const* src, int64_t bytes, int blocks_per_peer,
-                           void* stream);
+                           void* const* signal_flags, int epoch, void* done_counters, void* stream);
+int sb200_peer_wait_flags(const void* flags, int n, int epoch, void* error_flag, void* stream);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

@@ -63,9 +63,14 @@ extern "C" int sb200_peer_copy_blocks(int n, void* const* dst, const int* dst_de
 struct SbPushPlan {
   void* dst[8];
   const void* src[8];
+  int* flag[8];  // where to signal "block k has landed" on its destination (NULL: no signalling)
   int n;
 };
-__global__ void __launch_bounds__(512) sb_push_blocks_kernel(SbPushPlan plan, long long count16) {
+#ifdef SB200_EMU
+static inline void __threadfence_system() {}
+#endif
+__global__ void __launch_bounds__(512)
+    sb_push_blocks_kernel(SbPushPlan plan, long long count16, int epoch, int* done) {
   const int k = blockIdx.y;
   const float4* __restrict__ s = reinterpret_cast<const float4*>(plan.src[k]);
   float4* __restrict__ d = reinterpret_cast<float4*>(plan.dst[k]);
@@ -80,22 +85,67 @@ __global__ void __launch_bounds__(512) sb_push_blocks_kernel(SbPushPlan plan, lo
     d[i + 3 * stride] = e;
   }
   for (; i < count16; i += stride) d[i] = s[i];
+  if (plan.flag[k] == nullptr) return;
+  // signal the destination once ALL thread blocks of this destination have stored their share:
+  // every thread makes its stores visible system-wide, the last block to arrive raises the flag
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(&done[k], 1);
+    if (arrived == (int)gridDim.x - 1) {
+      done[k] = 0;
+      __threadfence_system();
+      *reinterpret_cast<volatile int*>(plan.flag[k]) = epoch;
+    }
+  }
+}
+
+// wait (on the stream) until the n flags of this rank's buffer have reached `epoch`: every source rank
+// has finished writing its block.  A bounded spin: after ~2 s without progress the kernel gives up and
+// raises *error instead of hanging the device.
+__global__ void sb_wait_flags_kernel(const int* flags, int n, int epoch, int* error) {
+  const int k = threadIdx.x;
+  if (k >= n) return;
+#ifndef SB200_EMU
+  const volatile int* f = flags + k;
+  const long long t0 = clock64();
+  while (*f < epoch) {
+    if (clock64() - t0 > 4000000000LL) {
+      *error = 1;
+      break;
+    }
+    __nanosleep(64);
+  }
+  __threadfence_system();
+#else
+  if (flags[k] < epoch) *error = 1;
+#endif
 }
 
 extern "C" int sb200_peer_push_blocks(int n, void* const* dst, const void* const* src, int64_t bytes,
-                                      int blocks_per_peer, void* stream) {
+                                      int blocks_per_peer, void* const* signal_flags, int epoch, void* done_counters,
+                                      void* stream) {
   SB_REQUIRE(n >= 0 && n <= 8 && dst && src, "peer_push_blocks: bad arguments (at most 8 blocks)");
   SB_REQUIRE(bytes % 16 == 0, "peer_push_blocks: block size must be a multiple of 16 bytes");
+  SB_REQUIRE(signal_flags == nullptr || done_counters != nullptr, "peer_push_blocks: signalling needs the counters");
   if (n == 0 || bytes == 0) return 0;
   SbPushPlan plan;
   plan.n = n;
-  for (int k = 0; k < n; ++k) {
-    plan.dst[k] = dst[k];
-    plan.src[k] = src[k];
+  for (int k = 0; k < 8; ++k) {
+    plan.dst[k] = k < n ? dst[k] : nullptr;
+    plan.src[k] = k < n ? src[k] : nullptr;
+    plan.flag[k] = (k < n && signal_flags) ? (int*)signal_flags[k] : nullptr;
   }
   if (blocks_per_peer <= 0) blocks_per_peer = 8;
-  SB_LAUNCH(sb_push_blocks_kernel, dim3((unsigned)blocks_per_peer, (unsigned)n), dim3(512), 0, stream, plan,
-            (long long)(bytes / 16));
+  SB_LAUNCH_COOP(sb_push_blocks_kernel, dim3((unsigned)blocks_per_peer, (unsigned)n), dim3(512), 0, stream, plan,
+                 (long long)(bytes / 16), epoch, (int*)done_counters);
   SB_CHECK_LAUNCH("peer_push_blocks");
+  return 0;
+}
+
+extern "C" int sb200_peer_wait_flags(const void* flags, int n, int epoch, void* error_flag, void* stream) {
+  SB_REQUIRE(flags && error_flag && n >= 1 && n <= 32, "peer_wait_flags: bad arguments");
+  SB_LAUNCH(sb_wait_flags_kernel, dim3(1), dim3(32), 0, stream, (const int*)flags, n, epoch, (int*)error_flag);
+  SB_CHECK_LAUNCH("peer_wait_flags");
   return 0;
 }

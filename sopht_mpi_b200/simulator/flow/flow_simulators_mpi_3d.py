@@ -287,6 +287,7 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
             rhs_vector_field=self.vorticity_field,
         )
         if not self.use_fused_kernels:
+            self.mpi_ghost_exchange_communicator.mark_stale(self.velocity_field)
             self.curl(curl=self.velocity_field, field=self.stream_func_field,
                       prefactor=self.real_t(0.5 / self.dx))
             self.update_velocity_with_free_stream(free_stream_velocity=free_stream_velocity)
@@ -305,6 +306,7 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
                  dptr(self.stream_func_field.tensor), float(self.real_t(0.5 / self.dx)), fs,
                  dptr(forcing), dptr(self._max_abs_vel_dev), ctx.stream())
         self._max_abs_vel_version = self.velocity_field.version
+        self.mpi_ghost_exchange_communicator.mark_stale(self.velocity_field)
         self._publish_max_abs_vel()
 
     def _publish_max_abs_vel(self):
@@ -359,7 +361,10 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
             # ghost planes of omega and u stand in for the reference's exchanges of u x omega
             # and of omega between its three sweeps
             ctx.exchange_vector(w)
-            ctx.exchange_vector(u)
+            # (the interactor has usually just exchanged the velocity: its ghost planes are current)
+            if not self.mpi_ghost_exchange_communicator.is_fresh(self.velocity_field):
+                self.mpi_ghost_exchange_communicator.exchange_vector_field_init(self.velocity_field)
+                self.mpi_ghost_exchange_communicator.exchange_finalise()
         alt = self._vorticity_alt
         ctx.call("sb200_vorticity_rhs_fused_3d", ctx.gref, dptr(alt), dptr(w), dptr(u), None,
                  float(self.real_t(dt / (2 * self.dx))),

@@ -100,6 +100,8 @@ class ImmersedBodyFlowInteractionMPI(VirtualBoundaryForcingMPI):
     def _update_lagrangian_kinematics(self):
         self.forcing_grid.compute_lag_grid_position_field()
         self.forcing_grid.compute_lag_grid_velocity_field()
+        # optional protocol of this build (see VirtualBoundaryForcingMPI._upload_kinematics)
+        self._kinematics_version = getattr(self.forcing_grid, "kinematics_version", None)
 
     def _compute_interaction_on_lag_grid_without_ghosting(self):
         """Forces on the Lagrangian points only (the body's sub-steps between two flow steps)."""

@@ -54,16 +54,23 @@ class EmptyForcingGrid(ImmersedBodyForcingGrid):
 class PrescribedForcingGrid(ImmersedBodyForcingGrid):
     """Lagrangian points with prescribed kinematics (synthetic bodies for benchmarks and
     tests): positions/velocities are whatever the owner wrote into the arrays; forces are
-    summed onto a single body node."""
+    summed onto a single body node.  With ``static=True`` the grid publishes a
+    ``kinematics_version`` that only changes when the owner calls :meth:`mark_moved` after rewriting
+    the arrays, so the interactor does not upload an unchanged body again."""
 
     def __init__(self, grid_dim, position_field, velocity_field=None, max_lag_grid_dx=None,
-                 centre=None):
+                 centre=None, static=False):
         super().__init__(grid_dim=grid_dim, num_lag_nodes=position_field.shape[-1])
+        self.kinematics_version = 0 if static else None
         self.position_field = np.array(position_field)
         self.velocity_field = (np.zeros_like(self.position_field) if velocity_field is None
                                else np.array(velocity_field, dtype=self.position_field.dtype))
         self.max_lag_grid_dx = max_lag_grid_dx
         self.centre = (self.position_field.mean(axis=1) if centre is None else np.asarray(centre))
+
+    def mark_moved(self):
+        if self.kinematics_version is not None:
+            self.kinematics_version += 1
 
     def compute_lag_grid_position_field(self):
         pass

@@ -251,6 +251,9 @@ class MPIGhostCommunicator:
         self.grid_coord = np.array(mpi_construct.grid.coords)
         self.comm_requests = []
         self._recv_staging = []
+        # fields whose ghost planes are known to be current: (data_ptr, host-write version) of the last
+        # exchange; the owner of a field drops the entry when a kernel rewrites it (``mark_stale``)
+        self._fresh = {}
 
     # -- local periodic wrap of the undivided axes (only for periodic domains)
     def _wrap_local_axes(self, t):
@@ -308,11 +311,32 @@ class MPIGhostCommunicator:
     def exchange_vector_field_init(self, local_vector_field):
         t, _ = _tensor_of(local_vector_field)
         self._exchange_init([t[c] for c in range(t.shape[0])])
+        if isinstance(local_vector_field, DeviceField):
+            self.mark_fresh(local_vector_field)
 
     def exchange_finalise(self):
         for req in self.comm_requests:
             req.wait()
         self.comm_requests = []
+
+    # ---- ghost freshness (B200 build): lets the simulator skip an exchange of a field whose ghost
+    # planes were filled since it was last written (the interactor exchanges the velocity right before
+    # the flow step exchanges it again)
+    @staticmethod
+    def _fresh_key(field):
+        t = getattr(field, "tensor", field)
+        return (t.data_ptr() if isinstance(t, torch.Tensor) else id(t), getattr(field, "version", None))
+
+    def mark_fresh(self, field):
+        ptr, version = self._fresh_key(field)
+        self._fresh[ptr] = version
+
+    def mark_stale(self, field):
+        self._fresh.pop(self._fresh_key(field)[0], None)
+
+    def is_fresh(self, field):
+        ptr, version = self._fresh_key(field)
+        return ptr in self._fresh and self._fresh[ptr] == version and version is not None
 
 
 class MPIFieldCommunicator:

@@ -7,8 +7,13 @@ through the NVSwitch, followed by a tiny NCCL all-reduce that orders "all blocks
 every rank's stream.  Replaces the MPI ``Alltoallw`` inside mpi4py-fft's transposes (reference
 ``poisson_solver_3d/fft_mpi_3d.py:27-48``).
 
-``SB200_EXCHANGE`` selects the transport for measurements: ``push`` (default), ``copy`` (one
-``cudaMemcpyPeerAsync`` per destination on the stream, round 1), ``nccl`` (all-to-all).  If CUDA IPC is
+"All blocks have landed" is signalled through peer memory too: the last thread block of every
+destination raises an epoch flag in the destination's memory, and a one-warp kernel on the
+destination's stream waits for the P flags (bounded spin), so no collective sits on the critical path.
+
+``SB200_EXCHANGE`` selects the transport for measurements: ``push`` (default), ``push-nccl`` (push kernel +
+a one-element NCCL all-reduce as the barrier), ``copy`` (one ``cudaMemcpyPeerAsync`` per destination on
+the stream + all-reduce, round 1), ``nccl`` (all-to-all).  If CUDA IPC is
 not available (different nodes, no peer access) the exchange falls back to NCCL.
 """
 import os
@@ -32,6 +37,11 @@ class PeerExchange:
         self.peer = None
         self._plans = {}
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        # epoch flags [buffer][source rank] (written by the peers), arrival counters of the push kernel
+        self.flags = torch.zeros((n_buffers, max(nranks, 1)), dtype=torch.int32, device=device)
+        self._done = torch.zeros((n_buffers, 8), dtype=torch.int32, device=device)
+        self._err = torch.zeros(1, dtype=torch.int32, device=device)
+        self._epoch = [0] * n_buffers
         self.transport = os.environ.get("SB200_EXCHANGE", "push")
         self.blocks_per_peer = int(os.environ.get("SB200_PUSH_BLOCKS", "0"))
         if self.transport == "nccl":
@@ -50,15 +60,18 @@ class PeerExchange:
             self.peer = None
 
     def _map_peers(self):
-        handles = [reduce_tensor(t) for t in self.local]
+        handles = [reduce_tensor(t) for t in self.local] + [reduce_tensor(self.flags)]
         gathered = [None] * self.nranks
         dist.all_gather_object(gathered, handles, group=host_group())
-        self.peer = []
+        self.peer, self.peer_flags = [], []
         for q in range(self.nranks):
             if q == self.rank:
                 self.peer.append(self.local)
+                self.peer_flags.append(self.flags)
             else:
-                self.peer.append([fn(*args) for fn, args in gathered[q]])
+                rebuilt = [fn(*args) for fn, args in gathered[q]]
+                self.peer.append(rebuilt[:-1])
+                self.peer_flags.append(rebuilt[-1])
         self._keep = gathered  # the rebuilt storages reference the senders' handles
         self._lib = _lib.load()
         self._dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -96,13 +109,30 @@ class PeerExchange:
             dptr = (ctypes.c_void_p * nranks)(*[self.peer[q][dst].chunk(nranks)[rank].data_ptr() for q in order])
             ddev = (ctypes.c_int * nranks)(*[self._peer_dev[q] for q in order])
             sptr = (ctypes.c_void_p * nranks)(*[s_blocks[q].data_ptr() for q in order])
-            plan = self._plans[(dst, src)] = (dptr, ddev, sptr, s_blocks[0].numel() * 4)
-        dptr, ddev, sptr, nbytes = plan
+            # where to signal on each destination: its flags[dst][this rank]
+            fptr = (ctypes.c_void_p * nranks)(*[self.peer_flags[q][dst, rank:rank + 1].data_ptr() for q in order])
+            plan = self._plans[(dst, src)] = (dptr, ddev, sptr, s_blocks[0].numel() * 4, fptr)
+        dptr, ddev, sptr, nbytes, fptr = plan
         if self.transport == "copy":
             _lib.check(self._lib, self._lib.sb200_peer_copy_blocks(nranks, dptr, ddev, sptr, self._dev, nbytes, stream))
-        else:
+        elif self.transport == "push-nccl":
             _lib.check(self._lib, self._lib.sb200_peer_push_blocks(nranks, dptr, sptr, nbytes, self.blocks_per_peer,
-                                                                  stream))
+                                                                  None, 0, None, stream))
+        else:
+            self._epoch[dst] += 1
+            epoch = self._epoch[dst]
+            _lib.check(self._lib, self._lib.sb200_peer_push_blocks(
+                nranks, dptr, sptr, nbytes, self.blocks_per_peer, fptr, epoch,
+                ctypes.c_void_p(self._done[dst].data_ptr()), stream))
+            _lib.check(self._lib, self._lib.sb200_peer_wait_flags(
+                ctypes.c_void_p(self.flags[dst].data_ptr()), nranks, epoch, ctypes.c_void_p(self._err.data_ptr()),
+                stream))
+            return
         # all ranks' copies precede their all-reduce in stream order: past this point every block of
         # `dst` has landed here, and every rank has finished reading the `src` blocks it was sent
         dist.all_reduce(self._flag)
+
+    def check(self):
+        """raise if a wait ever timed out (synchronises)"""
+        if int(self._err.item()) != 0:
+            raise _lib.SophtB200Error("peer exchange: a rank did not deliver its blocks in time")

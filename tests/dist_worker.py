@@ -107,7 +107,7 @@ def check_block_exchange():
 
     rank, size = dist.get_rank(), dist.get_world_size()
     ex = PeerExchange(2, 6 * size, torch.device("cpu"), rank, size, use_peer_copies=False)
-    assert ex.mode == "nccl send/recv"
+    assert ex.mode == "nccl all-to-all"
     ex.local[0].copy_(torch.arange(6 * size, dtype=torch.float32) + 100 * rank)
     try:
         ex.exchange(1, 0)
