@@ -575,7 +575,7 @@ def main():
 
         def e2e_api(i):
             fg.position_field[...] = pos_a if i % 2 else pos_b
-            fg.mark_moved()
+            getattr(fg, "mark_moved", lambda: None)()  # (ranks other than the master hold an empty grid)
             one_step()
             sink[...] = np.asarray(interactor.global_lag_grid_forcing_field).sum(axis=1)  # host read of the forces
             sink[0] += sim.get_max_vorticity()
@@ -589,7 +589,7 @@ def main():
                "full_field_io_value": measure(e2e_fields),
                "full_field_io_bytes_per_step": {"h2d": field_bytes, "d2h": 2 * field_bytes}}
         fg.position_field[...] = pos_a
-        fg.mark_moved()
+        getattr(fg, "mark_moved", lambda: None)()
     else:
         e2e = {"value": measure(e2e_fields), "unit": UNIT, "h2d_bytes_per_step": field_bytes,
                "d2h_bytes_per_step": 2 * field_bytes,

@@ -63,29 +63,65 @@ SB_D TL sb_support_scaled(const SbIbP<TL>& P, long long nearest, int off, TL pos
   return (TL)s / (TL)P.dx;
 }
 
-// The 1D delta factors of one point: lane 4 d + k holds the factor of window offset k along axis d
-// (12 evaluations per point instead of 3 per window cell; the per-cell weight is the same product
-// prefac * f_x * f_y * f_z in the same order, so the weights are unchanged bit for bit).
+// Eight lanes per Lagrangian point (four points per warp): lane `sub` of a group owns the window cells
+//   3D: kz = sub >> 1, ky in {2 (sub & 1), 2 (sub & 1) + 1}, kx = 0..3      (8 of the 64 cells)
+//   2D: ky = sub >> 1, kx in {2 (sub & 1), 2 (sub & 1) + 1}                  (2 of the 16 cells)
+// The twelve 1D delta factors of a point are evaluated once (lane sub: factor `sub`, lanes 0..3 also
+// factor 8 + sub) and handed round the group with shuffles; the per-cell weight is the product
+// prefac * f_x * f_y * f_z in the reference's order, so the weights are unchanged bit for bit.
 template <typename TL>
-SB_D TL sb_lane_delta(const SbIbP<TL>& P, const long long (&near)[3], const TL (&p)[3], unsigned lane) {
-  const int d = (int)(lane >> 2), k = (int)(lane & 3);
-  if (d >= P.dim) return TL(0);
-  const long long nd = d == 0 ? near[0] : d == 1 ? near[1] : near[2];
-  const TL pd = d == 0 ? p[0] : d == 1 ? p[1] : p[2];
-  return sb_delta_1d(P, sb_support_scaled(P, nd, k - P.width + 1, pd, d));
-}
+struct SbIbCells {
+  int kx[8], ky[8], kz[8], n;
+};
 template <typename TE, typename TL>
-SB_D TL sb_cell_weight(const SbIbP<TL>& P, TL lane_delta, int kx, int ky, int kz) {
-  const TL fx = __shfl_sync(0xffffffffu, lane_delta, kx);
-  const TL fy = __shfl_sync(0xffffffffu, lane_delta, 4 + ky);
-  const TL fz = __shfl_sync(0xffffffffu, lane_delta, 8 + kz);
-  TL w = P.weight_prefac * fx;
-  w = w * fy;
-  if (P.dim == 3) w = w * fz;
-  // the reference's Peskin kernel hands back weights rounded to real_t even when the Lagrangian
-  // arrays are wider (tests/golden/ib_*_f32_f64.npz: every w_pes value is a float32 number)
-  if (P.kernel_type == 1) w = (TL)(TE)w;
-  return w;
+SB_D void sb_group_weights(const SbIbP<TL>& P, const long long (&near)[3], const TL (&p)[3], unsigned lane,
+                           TL (&w)[8], int (&ck)[8][3], int& ncell) {
+  const unsigned sub = lane & 7u, base = lane & ~7u;
+  // factor `sub` (axes x: 0..3, y: 4..7) and, on lanes 0..3, factor 8 + sub (axis z)
+  TL fa, fb = TL(0);
+  {
+    const int d = (int)(sub >> 2), k = (int)(sub & 3);
+    fa = sb_delta_1d(P, sb_support_scaled(P, d == 0 ? near[0] : near[1], k - P.width + 1, d == 0 ? p[0] : p[1], d));
+    if (P.dim == 3 && sub < 4) fb = sb_delta_1d(P, sb_support_scaled(P, near[2], (int)sub - P.width + 1, p[2], 2));
+  }
+  TL fx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) fx[k] = __shfl_sync(0xffffffffu, fa, base + k);
+  if (P.dim == 3) {
+    const int kz = (int)(sub >> 1), ky0 = 2 * (int)(sub & 1);
+    const TL fy0 = __shfl_sync(0xffffffffu, fa, base + 4 + ky0), fy1 = __shfl_sync(0xffffffffu, fa, base + 5 + ky0);
+    const TL fz = __shfl_sync(0xffffffffu, fb, base + kz);
+    ncell = 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kx = i & 3, ky = ky0 + (i >> 2);
+      TL v = P.weight_prefac * fx[kx];
+      v = v * (i < 4 ? fy0 : fy1);
+      v = v * fz;
+      // the reference's Peskin kernel hands back weights rounded to real_t even when the Lagrangian
+      // arrays are wider (tests/golden/ib_*_f32_f64.npz: every w_pes value is a float32 number)
+      if (P.kernel_type == 1) v = (TL)(TE)v;
+      w[i] = v;
+      ck[i][0] = kx;
+      ck[i][1] = ky;
+      ck[i][2] = kz;
+    }
+  } else {
+    const int ky = (int)(sub >> 1), kx0 = 2 * (int)(sub & 1);
+    const TL fy = __shfl_sync(0xffffffffu, fa, base + 4 + ky);
+    ncell = 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kx = kx0 + (i & 1);
+      TL v = P.weight_prefac * ((i & 1) ? (kx0 ? fx[3] : fx[1]) : (kx0 ? fx[2] : fx[0]));
+      v = v * fy;
+      if (P.kernel_type == 1) v = (TL)(TE)v;
+      w[i] = v;
+      ck[i][0] = kx;
+      ck[i][1] = ky;
+      ck[i][2] = 0;
+    }
+  }
 }
 
 template <typename TE, typename TL, typename TC>
@@ -94,18 +130,11 @@ __global__ void __launch_bounds__(128)
                           const TL* vel, const TL* dpos, long long* nearest_out, TL* weights_out,
                           TL* flow_vel, TL* dvel, TL* force, double dx_pow_dim, TL kcoef, TL ccoef,
                           const int* __restrict__ owner, int my_rank) {
-  const unsigned lane = threadIdx.x & 31;
-  const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pt >= n) return;  // whole warp exits together
-  if (owner && owner[pt] != my_rank) {
-    // another rank's point: zeros, so that a SUM all-reduce over the ranks assembles the global arrays
-    if (lane == 0)
-      for (int c = 0; c < ncomp; ++c) {
-        flow_vel[c * n + pt] = TL(0);
-        if (force) dvel[c * n + pt] = force[c * n + pt] = TL(0);
-      }
-    return;
-  }
+  const unsigned lane = threadIdx.x & 31, sub = lane & 7u;
+  const long long pt0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const bool live = pt0 < n;
+  const long long pt = live ? pt0 : n - 1;  // (idle groups repeat the last point and store nothing)
+  const bool mine = !(owner && owner[pt] != my_rank);
   const int dim = P.dim, kw = 2 * P.width;
   long long near[3] = {0, 0, 0};
   TL p[3] = {0, 0, 0};
@@ -113,29 +142,37 @@ __global__ void __launch_bounds__(128)
     p[d] = pos[d * n + pt];
     near[d] = sb_nearest<TL, TC>(P, p[d], d);
   }
-  if (nearest_out && lane == 0)
-    for (int d = 0; d < dim; ++d) nearest_out[d * n + pt] = near[d];
-  const int ncell = dim == 3 ? kw * kw * kw : kw * kw;
+  TL w[8];
+  int ck[8][3], ncell;
+  sb_group_weights<TE, TL>(P, near, p, lane, w, ck, ncell);
   double acc[3] = {0.0, 0.0, 0.0};
-  const TL lane_delta = sb_lane_delta<TL>(P, near, p, lane);
-  for (int cell0 = 0; cell0 < ncell; cell0 += 32) {  // (uniform trip count: the weights are shuffled)
-    const int cell = cell0 + (int)lane;
-    const int kx = cell % kw, ky = (cell / kw) % kw, kz = (cell / (kw * kw)) % kw;
-    const int off0 = -P.width + 1;
-    const TL w = sb_cell_weight<TE, TL>(P, lane_delta, kx, ky, kz);
-    if (cell >= ncell) continue;
-    if (weights_out) weights_out[(long long)cell * n + pt] = w;
-    const long long x = near[0] + kx + off0, y = near[1] + ky + off0;
-    const long long z = dim == 3 ? near[2] + kz + off0 : 0;
-    if (x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz) {
-      const long long i = (z * g.my + y) * g.mx + x;
-      for (int c = 0; c < ncomp; ++c) acc[c] += (double)eul[i + c * g.vol] * (double)w;
+  const int off0 = -P.width + 1;
+  if (live && mine) {
+    if (nearest_out && sub == 0)
+      for (int d = 0; d < dim; ++d) nearest_out[d * n + pt] = near[d];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= ncell) break;
+      const int cell = (ck[i][2] * kw + ck[i][1]) * kw + ck[i][0];
+      if (weights_out) weights_out[(long long)cell * n + pt] = w[i];
+      const long long x = near[0] + ck[i][0] + off0, y = near[1] + ck[i][1] + off0;
+      const long long z = dim == 3 ? near[2] + ck[i][2] + off0 : 0;
+      if (x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz) {
+        const long long idx = (z * g.my + y) * g.mx + x;
+        for (int c = 0; c < ncomp; ++c) acc[c] += (double)eul[idx + c * g.vol] * (double)w[i];
+      }
     }
   }
   for (int c = 0; c < ncomp; ++c)
-    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-  if (lane == 0) {
+    for (int o = 4; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  if (live && sub == 0) {
     for (int c = 0; c < ncomp; ++c) {
+      if (!mine) {
+        // another rank's point: zeros, so that a SUM all-reduce over the ranks assembles the global arrays
+        flow_vel[c * n + pt] = TL(0);
+        if (force) dvel[c * n + pt] = force[c * n + pt] = TL(0);
+        continue;
+      }
       const TL u = (TL)(acc[c] * dx_pow_dim);
       flow_vel[c * n + pt] = u;
       if (force) {
@@ -152,10 +189,11 @@ __global__ void __launch_bounds__(128)
     sb_ib_spread_kernel(SbGeom g, SbIbP<TL> P, long long n, TE* eul, const TL* lag, const TL* pos,
                         const int* __restrict__ owner, int my_rank) {
   const unsigned lane = threadIdx.x & 31;
-  const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pt >= n) return;
-  if (owner && owner[pt] != my_rank) return;
-  const int dim = P.dim, kw = 2 * P.width;
+  const long long pt0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const bool live = pt0 < n;
+  const long long pt = live ? pt0 : n - 1;
+  const bool mine = !(owner && owner[pt] != my_rank);
+  const int dim = P.dim;
   long long near[3] = {0, 0, 0};
   TL p[3] = {0, 0, 0}, f[3] = {0, 0, 0};
   for (int d = 0; d < dim; ++d) {
@@ -163,19 +201,19 @@ __global__ void __launch_bounds__(128)
     f[d] = lag[d * n + pt];
     near[d] = sb_nearest<TL, TC>(P, p[d], d);
   }
-  const int ncell = dim == 3 ? kw * kw * kw : kw * kw;
-  const TL lane_delta = sb_lane_delta<TL>(P, near, p, lane);
-  for (int cell0 = 0; cell0 < ncell; cell0 += 32) {
-    const int cell = cell0 + (int)lane;
-    const int kx = cell % kw, ky = (cell / kw) % kw, kz = (cell / (kw * kw)) % kw;
-    const int off0 = -P.width + 1;
-    const TL w = sb_cell_weight<TE, TL>(P, lane_delta, kx, ky, kz);
-    if (cell >= ncell) continue;
-    const long long x = near[0] + kx + off0, y = near[1] + ky + off0;
-    const long long z = dim == 3 ? near[2] + kz + off0 : 0;
+  TL w[8];
+  int ck[8][3], ncell;
+  sb_group_weights<TE, TL>(P, near, p, lane, w, ck, ncell);
+  if (!(live && mine)) return;
+  const int off0 = -P.width + 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i >= ncell) break;
+    const long long x = near[0] + ck[i][0] + off0, y = near[1] + ck[i][1] + off0;
+    const long long z = dim == 3 ? near[2] + ck[i][2] + off0 : 0;
     if (x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz) {
-      const long long i = (z * g.my + y) * g.mx + x;
-      for (int c = 0; c < dim; ++c) atomicAdd(&eul[i + c * g.vol], (TE)(f[c] * w));
+      const long long idx = (z * g.my + y) * g.mx + x;
+      for (int c = 0; c < dim; ++c) atomicAdd(&eul[idx + c * g.vol], (TE)(f[c] * w[i]));
     }
   }
 }
@@ -224,8 +262,8 @@ static int ib_interact_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, lon
   } else {
     for (int k = 0; k < gr->dim; ++k) dxp *= p->dx;
   }
-  const int warps = 4;
-  dim3 block(32 * warps), grid((unsigned)((n + warps - 1) / warps));
+  const int warps = 4, per_block = 4 * warps;  // four points per warp
+  dim3 block(32 * warps), grid((unsigned)((n + per_block - 1) / per_block));
   SB_LAUNCH_COOP((sb_ib_interact_kernel<TE, TL, TC>), grid, block, 0, stream, g, P, n, ncomp,
                  (const TE*)eul, (const TL*)pos, (const TL*)vel, (const TL*)dpos, (long long*)nearest,
                  (TL*)weights, (TL*)flow_vel, (TL*)dvel, (TL*)force, dxp, (TL)p->stiffness,
@@ -244,8 +282,8 @@ static int ib_spread_t(const sb200_grid_t* gr, const sb200_ib_params_t* p, long 
   SbIbP<TL> P;
   sb_make_ib<TL>(gr, p, &P);
   if (n <= 0) return 0;
-  const int warps = 4;
-  dim3 block(32 * warps), grid((unsigned)((n + warps - 1) / warps));
+  const int warps = 4, per_block = 4 * warps;
+  dim3 block(32 * warps), grid((unsigned)((n + per_block - 1) / per_block));
   SB_LAUNCH_COOP((sb_ib_spread_kernel<TE, TL, TC>), grid, block, 0, stream, g, P, n, (TE*)eul,
                  (const TL*)lag, (const TL*)pos, owner, my_rank);
   SB_CHECK_LAUNCH("ib_spread");

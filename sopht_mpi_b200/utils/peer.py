@@ -76,12 +76,13 @@ class PeerExchange:
         self._lib = _lib.load()
         self._dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._peer_dev = [self.peer[q][0].device.index for q in range(self.nranks)]
-        if self.transport == "copy":
-            for q in range(self.nranks):
-                if q != self.rank:
-                    # both directions: without the reverse mapping the driver stages the copy through
-                    # the host (25 GB/s instead of ~640 GB/s, profiles/r01_peer_copy.txt)
-                    _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._dev, self._peer_dev[q]))
+        for q in range(self.nranks):
+            if q != self.rank:
+                # this device -> peer: the push kernel stores through the mapped pointers
+                _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._dev, self._peer_dev[q]))
+                if self.transport == "copy":
+                    # copy engines: without the reverse mapping the driver stages the copy through the
+                    # host (25 GB/s instead of ~640 GB/s, profiles/r01_peer_copy.txt)
                     _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._peer_dev[q], self._dev))
 
     @property

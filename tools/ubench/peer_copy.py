@@ -48,6 +48,11 @@ def main():
     timed("pull cudaMemcpyPeerAsync", lambda: lib.sb200_peer_copy(
         ctypes.c_void_p(src.data_ptr()), rank, ctypes.c_void_p(peer.data_ptr()), 1 - rank, n, sp))
     timed("torch copy_ push", lambda: peer.copy_(src, non_blocking=True))
+    for bpp in (4, 8, 16, 32, 64):
+        dp = (ctypes.c_void_p * 1)(peer.data_ptr())
+        spp = (ctypes.c_void_p * 1)(src.data_ptr())
+        timed(f"push kernel ({bpp} blocks of 512 threads)", lambda: lib.sb200_peer_push_blocks(
+            1, dp, spp, n, bpp, None, 0, None, sp))
     other = torch.empty_like(src)
     timed("nccl send/recv", lambda: dist.batch_isend_irecv(
         [dist.P2POp(dist.isend, src, 1 - rank), dist.P2POp(dist.irecv, other, 1 - rank)])[-1].wait())
