@@ -95,6 +95,12 @@ int sb200_divergence(const sb200_grid_t* g, void* divergence, const void* field,
 /* stencil_ops_3d/laplacian_filter_mpi_3d.py:267-419; filter_type 0 = multiplicative, 1 = convolution */
 int sb200_laplacian_filter(const sb200_grid_t* g, void* field, int ncomp, int filter_order, int filter_type,
                            void* filter_flux_buffer, void* field_buffer, void* stream);
+/* The order-1 multiplicative filter (the rod examples' setting, flow_past_rod_case.py:114-115) of a
+ * vector field in ONE pass, out of place: out = field - Fz(Fy(Fx(field))) with the wrappers' masks and ring
+ * zeroing (laplacian_filter_mpi_3d.py:267-319), for a block whose six faces are all physical (one rank).
+ * filter_flux_buffer and field_buffer end up as the reference leaves them (the last component's flux). */
+int sb200_laplacian_filter_order1_out_of_place(const sb200_grid_t* g, void* out, const void* field, int ncomp,
+                                               void* filter_flux_buffer, void* field_buffer, void* stream);
 /* one axis pass of the filter incl. the ring clearing that follows it
  * (laplacian_filter_mpi_3d.py:145-264,118-143); axis = ARRAY axis counted from the
  * last one: 0 = x, 1 = y, 2 = z.  Lets the host exchange halos between passes. */

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "sb200_advection_timestep_eno3": (c_int, [_G, _V, c_int, _V, _V, c_double, _V]),
     "sb200_divergence": (c_int, [_G, _V, _V, c_double, _V]),
     "sb200_laplacian_filter": (c_int, [_G, _V, c_int, c_int, c_int, _V, _V, _V]),
+    "sb200_laplacian_filter_order1_out_of_place": (c_int, [_G, _V, _V, c_int, _V, _V, _V]),
     "sb200_laplacian_filter_axis": (c_int, [_G, _V, _V, c_int, _V]),
     "sb200_laplacian_filter_stage": (c_int, [_G, _V, _V, c_int, _V, c_int, _V]),
     "sb200_clear_physical_ring": (c_int, [_G, _V, c_int, c_int, _V]),

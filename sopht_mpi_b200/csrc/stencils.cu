@@ -4,6 +4,7 @@
 #include "sb200_common.h"
 
 #include <cstdarg>
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 void sb_set_error(const char* fmt, ...) {
@@ -605,6 +606,91 @@ extern "C" int sb200_clear_physical_ring(const sb200_grid_t* gr, void* field, in
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
   SB_DISPATCH_DTYPE(gr->dtype, return sb_launch_cells(g, ClearRingOp<T>{(T*)field, ncomp, width}, stream,
                                                       "clear_ring"));
+}
+
+// ---- order-1 multiplicative filter in ONE pass (the setting of the rod examples,
+// examples/3d_examples/FlowPastRodCase/flow_past_rod_case.py:114-115) on a rank whose six faces are all
+// physical.  There every cell is either "deep" (written by each stage's interior call and outside
+// the zeroed ring) or in the ring, so the chain of FilterStageOp collapses to
+//     a = deep ? Fx(f) : 0,  b = deep ? Fy(a) : 0,  c = deep ? Fz(b) : 0,  f -= c
+// with F the 1D kernel 0.25 (-in(+1) - in(-1) + 2 in) (laplacian_filter_mpi_3d.py:62-99,267-319).  A block
+// stages an (8+2) x (8+2) x (32+2) tile (16+2 in double) of the field in shared memory and applies the three stages
+// there: 2 W per cell and component instead of 8 W + a copy.  OUT OF PLACE (a block reads a halo of
+// cells that belong to its neighbours): the simulator alternates between its two vorticity
+// allocations.  The last component also leaves the reference's buffer contents behind
+// (filter_flux_buffer = field_buffer = c).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sb_filter_o1_mult_kernel(SbGeom g, T* __restrict__ out, const T* __restrict__ field, int ncomp,
+                             T* __restrict__ flux, T* __restrict__ buf) {
+  constexpr int TX = sizeof(T) == 4 ? 32 : 16, TY = 8, TZ = 8;  // (static shared memory: <= 48 KB)
+  constexpr int FX = TX + 2, FY = TY + 2, FZ = TZ + 2;
+  __shared__ T sf[FZ * FY * FX];
+  __shared__ T sa[FZ * FY * TX];
+  __shared__ T sb[FZ * TY * TX];
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int nzt = (g.mz + TZ - 1) / TZ;
+  const int c = blockIdx.z / nzt, z0 = (blockIdx.z - c * nzt) * TZ;
+  const T* f = field + (long long)c * g.vol;
+  T* o = out + (long long)c * g.vol;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FZ * FY * FX; i += 256) {
+    const int lx = i % FX, r = i / FX, ly = r % FY, lz = r / FY;
+    const int x = x0 + lx - 1, y = y0 + ly - 1, z = z0 + lz - 1;
+    const bool in = x >= 0 && x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz;
+    sf[i] = in ? f[g.idx(z, y, x)] : T(0);
+  }
+  __syncthreads();
+  for (int i = tid; i < FZ * FY * TX; i += 256) {
+    const int lx = i % TX, r = i / TX, ly = r % FY, lz = r / FY;
+    const int x = x0 + lx, y = y0 + ly - 1, z = z0 + lz - 1;
+    const bool in = x < g.mx && y >= 0 && y < g.my && z >= 0 && z < g.mz;
+    const T* q = sf + (lz * FY + ly) * FX + lx + 1;
+    sa[i] = (in && g.deep(z, y, x)) ? T(0.25) * (-q[1] - q[-1] + T(2) * q[0]) : T(0);
+  }
+  __syncthreads();
+  for (int i = tid; i < FZ * TY * TX; i += 256) {
+    const int lx = i % TX, r = i / TX, ly = r % TY, lz = r / TY;
+    const int x = x0 + lx, y = y0 + ly, z = z0 + lz - 1;
+    const bool in = x < g.mx && y < g.my && z >= 0 && z < g.mz;
+    const T* q = sa + (lz * FY + ly + 1) * TX + lx;
+    sb[i] = (in && g.deep(z, y, x)) ? T(0.25) * (-q[TX] - q[-TX] + T(2) * q[0]) : T(0);
+  }
+  __syncthreads();
+  const bool last = c == ncomp - 1;
+  for (int i = tid; i < TZ * TY * TX; i += 256) {
+    const int lx = i % TX, r = i / TX, ly = r % TY, lz = r / TY;
+    const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
+    if (x >= g.mx || y >= g.my || z >= g.mz) continue;
+    const T* q = sb + ((lz + 1) * TY + ly) * TX + lx;
+    const T cz = g.deep(z, y, x) ? T(0.25) * (-q[TY * TX] - q[-TY * TX] + T(2) * q[0]) : T(0);
+    const long long gi = g.idx(z, y, x);
+    o[gi] = sf[((lz + 1) * FY + ly + 1) * FX + lx + 1] - cz;
+    if (last) {  // (the reference copies the flux into field_buffer after every stage)
+      flux[gi] = cz;
+      buf[gi] = cz;
+    }
+  }
+}
+template <typename T>
+static int launch_filter_o1_mult(const SbGeom& g, void* out, const void* field, int ncomp, void* flux, void* buf,
+                                 void* stream) {
+  constexpr int TX = sizeof(T) == 4 ? 32 : 16;
+  const dim3 grid((unsigned)((g.mx + TX - 1) / TX), (unsigned)((g.my + 7) / 8), (unsigned)(((g.mz + 7) / 8) * ncomp));
+  SB_LAUNCH_COOP(sb_filter_o1_mult_kernel<T>, grid, dim3(256), 0, stream, g, (T*)out, (const T*)field, ncomp,
+                 (T*)flux, (T*)buf);
+  SB_CHECK_LAUNCH("filter_o1_mult");
+  return 0;
+}
+
+extern "C" int sb200_laplacian_filter_order1_out_of_place(const sb200_grid_t* gr, void* out, const void* field,
+                                                          int ncomp, void* flux, void* buf, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.dim == 3 && g.gs >= 1 && ncomp >= 1 && ncomp <= 3, "filter_order1: 3D fields, ghost_size >= 1");
+  for (int k = 0; k < 6; ++k) SB_REQUIRE(g.phys[k], "filter_order1: every face of the block must be physical");
+  SB_REQUIRE(out && field && flux && buf && out != field, "filter_order1: bad pointers (out of place)");
+  SB_DISPATCH_DTYPE(gr->dtype, return launch_filter_o1_mult<T>(g, out, field, ncomp, flux, buf, stream));
 }
 
 extern "C" int sb200_laplacian_filter(const sb200_grid_t* gr, void* field, int ncomp, int filter_order,

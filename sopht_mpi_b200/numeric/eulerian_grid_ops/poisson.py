@@ -36,17 +36,30 @@ class _UnboundedPoissonSolver:
             small_enough = gs3[2] <= 4096 and gs3[1] <= 2048 and gs3[0] <= 2048
             backend = ("fft" if (pow2 and big_enough and small_enough
                                  and _fft_backend_available(self.lib)) else "cufft")
-        if mpi_construct.size > 1 and (backend != "fft" or dim != 3):
-            raise _lib.SophtB200Error(
-                "the distributed Poisson solve needs the fft backend: 3D power-of-two grids on "
-                "2, 4 or 8 z-slabs")
+        # Distributed solve.  The slab pipeline (transposes over NVLink, see _solve_slabs) covers 3D
+        # power-of-two grids on 2, 4 or 8 leading-axis slabs that are at least 2 ghost_size thick.
+        # Everything else the reference's mpi4py-fft path accepts (2D decompositions such as BASELINE
+        # configs[0]'s `-np 2` cylinder, other grid sizes, other rank counts) runs REPLICATED: the slab
+        # interiors are all-gathered over NCCL, every GPU solves the whole (then small or odd-sized)
+        # domain with the single-rank solver and keeps its own slab.
+        self.replicated = False
+        if mpi_construct.size > 1:
+            size = mpi_construct.size
+            lead = gs3[3 - dim]
+            slab_ok = (backend == "fft" and dim == 3 and size in (2, 4, 8) and lead % size == 0
+                       and lead // size >= 2 * ghost_size)
+            if not slab_ok:
+                self.replicated = True
+                if backend == "fft" and not all(_is_pow2(int(g)) for g in grid_size):
+                    backend = "cufft"
         self.backend = backend
         self._slab_bufs = []
         self._slab_events = None
         self._handle = ctypes.c_void_p()
+        lib_rank, lib_size = (0, 1) if self.replicated else (mpi_construct.rank, mpi_construct.size)
         _lib.check(self.lib, self.lib.sb200_poisson_create(
             ctypes.byref(self._handle), dim, _lib.dtype_code(real_t), gs3[0], gs3[1], gs3[2],
-            ghost_size, float(x_range), mpi_construct.rank, mpi_construct.size,
+            ghost_size, float(x_range), lib_rank, lib_size,
             1 if backend == "fft" else 0, current_stream_ptr(self.device)))
 
     def __del__(self):
@@ -89,9 +102,37 @@ class _UnboundedPoissonSolver:
         stream = current_stream_ptr(self.device)
         if self.mpi_construct.size == 1:
             _lib.check(self.lib, self.lib.sb200_poisson_solve(self._handle, dptr(s), dptr(r), ncomp, stream))
+        elif self.replicated:
+            self._solve_replicated(s, r, ncomp, stream)
         else:
             self._solve_slabs(s, r, ncomp, stream)
         st.finish()
+
+    def _solve_replicated(self, s, r, ncomp, stream):
+        """all-gather the slab interiors -> whole-domain solve on every GPU -> keep the own slab"""
+        import torch
+        import torch.distributed as dist
+
+        mc, gs, dim = self.mpi_construct, self.ghost_size, self.dim
+        size, rank = mc.size, mc.rank
+        inner = (slice(None),) + (slice(gs, -gs),) * dim
+        r_v = r if r.dim() == dim + 1 else r.unsqueeze(0)
+        s_v = s if s.dim() == dim + 1 else s.unsqueeze(0)
+        local = r_v[inner].contiguous()                    # (ncomp, n_lead / P, ...)
+        if getattr(self, "_rep_bufs", None) is None or self._rep_bufs[0].shape[1] != ncomp:
+            glob_shape = (ncomp,) + tuple(int(g) + 2 * gs for g in
+                                          (self.grid_size_z, self.grid_size_y, self.grid_size_x)[3 - dim:])
+            self._rep_bufs = (torch.empty((size,) + tuple(local.shape), dtype=local.dtype, device=local.device),
+                              torch.zeros(glob_shape, dtype=local.dtype, device=local.device),
+                              torch.zeros(glob_shape, dtype=local.dtype, device=local.device))
+        gathered, g_rhs, g_sol = self._rep_bufs
+        dist.all_gather_into_tensor(gathered, local)
+        n_lead = local.shape[1]
+        # (P, ncomp, n_lead_local, ...) -> (ncomp, P * n_lead_local, ...): slabs stack along the leading axis
+        g_rhs[inner].copy_(gathered.transpose(0, 1).reshape((ncomp, size * n_lead) + tuple(local.shape[2:])))
+        _lib.check(self.lib, self.lib.sb200_poisson_solve(self._handle, dptr(g_sol), dptr(g_rhs), ncomp, stream))
+        own = (slice(None), slice(gs + rank * n_lead, gs + (rank + 1) * n_lead)) + (slice(gs, -gs),) * (dim - 1)
+        s_v[inner].copy_(g_sol[own])
 
     def _solve_slabs(self, s, r, ncomp, stream):
         """z-slab solve: local x pass, all-to-all (z-slabs <-> kx-slabs, on the x-pass output: the

@@ -141,6 +141,7 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
             self.eul_grid_forcing_field = zeros_like(self.velocity_field)
         self._vorticity_alt = None
         self._forcing_tile_flags = None
+        self._one_pass_filter = False
         self._max_abs_vel_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._max_abs_vel_version = None
         # global max |u| of the last fused velocity sweep, reduced over the ranks and copied to pinned
@@ -204,6 +205,10 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
 
             self.filter_vector_field = filter_vector_field
             if self.filter_vorticity and self.filter_setting_dict is not None:
+                self._one_pass_filter = (
+                    self.use_fused_kernels and self.mpi_construct.size == 1
+                    and self.filter_setting_dict["order"] == 1
+                    and self.filter_setting_dict["type"] == "multiplicative" and self.ghost_size >= 1)
                 self.filter_vector_field = gen_laplacian_filter_mpi_kernel_3d(
                     mpi_construct=self.mpi_construct,
                     ghost_exchange_communicator=self.mpi_ghost_exchange_communicator,
@@ -345,9 +350,24 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
                 diffusion_flux=self.buffer_scalar_field,
                 nu_dt_by_dx2=self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx),
             )
-        self.filter_vector_field(vector_field=self.vorticity_field)
+        if self._one_pass_filter:
+            self._filter_vorticity_one_pass()
+        else:
+            self.filter_vector_field(vector_field=self.vorticity_field)
         self.compute_flow_velocity(free_stream_velocity=free_stream_velocity,
                                    reset_forcing=_reset_forcing)
+
+    def _filter_vorticity_one_pass(self):
+        """order-1 multiplicative filter in one out-of-place sweep (csrc/stencils.cu); like the fused
+        update, the result lands in the second vorticity allocation and the two swap roles"""
+        ctx = self._ctx
+        w = self.vorticity_field.tensor
+        if self._vorticity_alt is None:
+            self._vorticity_alt = torch.empty_like(w)
+        alt = self._vorticity_alt
+        ctx.call("sb200_laplacian_filter_order1_out_of_place", ctx.gref, dptr(alt), dptr(w), self.grid_dim,
+                 dptr(self.buffer_vector_field.tensor[0]), dptr(self.buffer_vector_field.tensor[1]), ctx.stream())
+        w.data, alt.data = alt.data, w.data
 
     def _fused_vorticity_update(self, dt):
         """cross product + curl update + diffusion in ONE streaming kernel (csrc/fused.cu).

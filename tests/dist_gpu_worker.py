@@ -145,10 +145,77 @@ def main():
     want = f_glob[:, rank * nzl + gs:rank * nzl + gs + nzl, gs:-gs, gs:-gs]
     assert np.abs(got - want).max() / np.abs(f_glob).max() <= 1e-5
 
+    check_replicated_solves(gs)
+
     dist.barrier()
     if rank == 0:
         print("DIST_GPU_WORKER_OK")
     dist.destroy_process_group()
+
+
+def check_replicated_solves(gs):
+    """Configurations outside the slab pipeline (a grid that is not a power of two; the 2D `-np P`
+    case of BASELINE configs[0]) run replicated: same results as the single-domain oracle."""
+    from oracle.poisson import UnboundedPoissonSolverOracle2D
+    from oracle.simulator import FlowSimulatorOracle2D
+    from sopht_mpi_b200.numeric.eulerian_grid_ops import UnboundedPoissonSolverMPI3D
+    from sopht_mpi_b200.simulator import UnboundedFlowSimulator2D
+    from sopht_mpi_b200.utils import MPIConstruct3D
+    from sopht_mpi_b200.utils.device import DeviceField
+
+    real_t = np.float64
+    size = dist.get_world_size()
+    n = (6 * size, 20, 36)
+    mc = MPIConstruct3D(*n, real_t=real_t, rank_distribution=(0, 1, 1))
+    rank = mc.rank
+    nzl = n[0] // size
+    rng = np.random.default_rng(4)
+    rhs = rng.uniform(size=(3, n[0] + 2 * gs, n[1] + 2 * gs, n[2] + 2 * gs)).astype(real_t)
+    ref = np.zeros_like(rhs)
+    UnboundedPoissonSolverOracle3D(*n, x_range=1.0, real_t=real_t).vector_field_solve(ref, rhs, gs)
+    solver = UnboundedPoissonSolverMPI3D(*n, mpi_construct=mc, ghost_size=gs, x_range=1.0, real_t=real_t)
+    assert solver.replicated and solver.backend == "cufft"
+    loc = np.ascontiguousarray(rhs[:, rank * nzl:rank * nzl + nzl + 2 * gs])
+    out = DeviceField(torch.full(loc.shape, 7.0, dtype=torch.float64, device=mc.device))
+    solver.vector_field_solve(solution_vector_field=out, rhs_vector_field=DeviceField(torch.from_numpy(loc).to(mc.device)))
+    got = np.asarray(out)
+    inner = (slice(None), slice(gs, -gs), slice(gs, -gs), slice(gs, -gs))
+    assert rel(got[inner], ref[:, rank * nzl + gs:rank * nzl + gs + nzl, gs:-gs, gs:-gs]) <= 1e-10
+    assert np.all(got[:, 0] == 7.0)  # ghosts untouched
+    one = DeviceField(torch.zeros(loc.shape[1:], dtype=torch.float64, device=mc.device))
+    solver.solve(solution_field=one, rhs_field=DeviceField(torch.from_numpy(np.ascontiguousarray(loc[1])).to(mc.device)))
+    assert rel(np.asarray(one)[inner[1:]], ref[1, rank * nzl + gs:rank * nzl + gs + nzl, gs:-gs, gs:-gs]) <= 1e-10
+
+    # 2D flow past a cylinder on y-slabs (BASELINE configs[0]: 2D, float64, mpirun -np 2)
+    n2 = (16 * size, 64)
+    kw = dict(grid_size=n2, x_range=1.0, kinematic_viscosity=3e-3, flow_type="navier_stokes_with_forcing",
+              real_t=real_t, with_free_stream_flow=True)
+    sim = UnboundedFlowSimulator2D(rank_distribution=(0, 1), **kw)
+    ora = FlowSimulatorOracle2D(**kw)
+    nyl = n2[0] // size
+    sl = slice(rank * nyl, rank * nyl + nyl + 2 * gs)
+    yy, xx = np.meshgrid(ora.local_y, ora.local_x, indexing="ij")
+    blob = np.exp(-((xx - 0.3) ** 2 + (yy - 0.5 * ora.local_y[-gs - 1]) ** 2) / 0.004)
+    ora.vorticity_field[...] = 3.0 * blob
+    sim.vorticity_field[...] = np.ascontiguousarray((3.0 * blob)[sl])
+    u_inf = [1.0, 0.0]
+    for c in range(2):
+        ora.velocity_field[c] += real_t(u_inf[c])
+    sim.velocity_field[...] = np.ascontiguousarray(ora.velocity_field[:, sl])
+    for step in range(3):
+        dt = ora.compute_stable_timestep()
+        assert abs(sim.compute_stable_timestep() - dt) <= 1e-10 * dt
+        force = np.stack([blob, -0.5 * blob]) * np.cos(2.0 * step)
+        force[:, :gs], force[:, -gs:], force[:, :, :gs], force[:, :, -gs:] = 0, 0, 0, 0
+        ora.eul_grid_forcing_field[...] = force
+        sim.eul_grid_forcing_field[...] = np.ascontiguousarray(force[:, sl])
+        ora.time_step(dt, free_stream_velocity=u_inf)
+        sim.time_step(dt=dt, free_stream_velocity=u_inf)
+    isl = slice(rank * nyl + gs, rank * nyl + gs + nyl)
+    for name in ("vorticity_field", "velocity_field", "stream_func_field"):
+        got = np.asarray(getattr(sim, name))[..., gs:-gs, gs:-gs]
+        want = getattr(ora, name)[..., isl, gs:-gs]
+        assert np.abs(got - want).max() / np.abs(getattr(ora, name)).max() <= 1e-10, name
 
 
 if __name__ == "__main__":

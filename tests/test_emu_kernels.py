@@ -573,3 +573,26 @@ def test_sparse_forcing_update_and_flagged_reset(dim, sparse):
     assert (n_active < nchunks) if sparse else (n_flagged == nchunks)
     call("sb200_clear_flagged_tiles", ctypes.byref(g), ptr(f), dim, ptr(work), None)
     assert not f.any() and not work.any()
+
+
+def test_one_pass_order1_multiplicative_filter(setup3d):
+    """sb200_laplacian_filter_order1_out_of_place == the reference's stage chain (field and both buffers)."""
+    real_t, rng, n, gs, shape, g = setup3d
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    ref = w.copy()
+    fb0, bb0 = rng.uniform(size=shape).astype(real_t), rng.uniform(size=shape).astype(real_t)
+    fb1, bb1 = fb0.copy(), bb0.copy()
+    st.laplacian_filter_mpi(ref, fb0, bb0, 1, "multiplicative", gs)
+    out = np.full_like(w, np.nan)
+    call("sb200_laplacian_filter_order1_out_of_place", ctypes.byref(g), ptr(out), ptr(w), 3, ptr(fb1), ptr(bb1), None)
+    assert np.array_equal(out, ref) and np.array_equal(fb1, fb0) and np.array_equal(bb1, bb0)
+    big = (20, 19, 70)  # several tiles along every axis
+    shape2 = tuple(v + 2 * gs for v in big)
+    g2 = _lib.make_grid(3, real_t, gs, big, [1] * 6)
+    w2 = rng.uniform(size=(3,) + shape2).astype(real_t)
+    ref2 = w2.copy()
+    a, b = np.zeros(shape2, real_t), np.zeros(shape2, real_t)
+    st.laplacian_filter_mpi(ref2, a, b, 1, "multiplicative", gs)
+    out2, a1, b1 = np.empty_like(w2), np.zeros(shape2, real_t), np.zeros(shape2, real_t)
+    call("sb200_laplacian_filter_order1_out_of_place", ctypes.byref(g2), ptr(out2), ptr(w2), 3, ptr(a1), ptr(b1), None)
+    assert np.array_equal(out2, ref2) and np.array_equal(a1, a)
