@@ -123,6 +123,21 @@ int sb200_clear_physical_ring(const sb200_grid_t* g, void* field, int ncomp, int
 int sb200_penalise_field_boundary(const sb200_grid_t* g, void* field, int ncomp, int width,
                                   const void* factors, void* stream);
 
+/* ---- operators of the reference API that no simulator path uses (arithmetic in the un-vendored `sopht`
+ * package, published forms restated):
+ * stencil_ops_3d/brinkmann_penalise_mpi_3d.py:7-21: penalised = (field + lambda chi target) / (1 + lambda chi),
+ * pointwise over `count` cells, `ncomp` components sharing one characteristic function;
+ * stencil_ops_3d/char_func_from_level_set_mpi_3d.py:8-30: smooth sine Heaviside of a level set;
+ * stencil_ops_3d/update_vorticity_from_velocity_forcing_mpi_3d.py:181-330:
+ * omega += prefactor * curl(penalised_velocity - velocity) on the cells the wrapper writes. */
+int sb200_brinkmann_penalise(int dtype, void* penalised, double penalty_factor, const void* char_func,
+                             const void* penalty_field, const void* field, int ncomp, int64_t count, void* stream);
+int sb200_char_func_from_level_set(int dtype, void* char_func, const void* level_set, double blend_width,
+                                   int64_t count, void* stream);
+int sb200_update_vorticity_from_penalised_velocity(const sb200_grid_t* g, void* vorticity,
+                                                   const void* penalised_velocity, const void* velocity,
+                                                   double prefactor, void* stream);
+
 /* ---- reductions over the interior; result written as ONE double at `out`
  * (device pointer, 8 bytes) ------------------------------------------------ */
 /* max over interior of sum_c |u_c| : simulator/flow/flow_simulators_mpi_3d.py:429-442 */

@@ -70,6 +70,9 @@ PROTOTYPES = {
     "sb200_laplacian_filter_stage": (c_int, [_G, _V, _V, c_int, _V, c_int, _V]),
     "sb200_clear_physical_ring": (c_int, [_G, _V, c_int, c_int, _V]),
     "sb200_penalise_field_boundary": (c_int, [_G, _V, c_int, c_int, _V, _V]),
+    "sb200_brinkmann_penalise": (c_int, [c_int, _V, c_double, _V, _V, _V, c_int, c_int64, _V]),
+    "sb200_char_func_from_level_set": (c_int, [c_int, _V, _V, c_double, c_int64, _V]),
+    "sb200_update_vorticity_from_penalised_velocity": (c_int, [_G, _V, _V, _V, c_double, _V]),
     "sb200_max_abs_sum": (c_int, [_G, _V, c_int, _V, _V]),
     "sb200_max": (c_int, [_G, _V, c_int, _V, _V]),
     "sb200_sum_squares": (c_int, [_G, _V, c_int, _V, _V]),

@@ -709,6 +709,90 @@ extern "C" int sb200_laplacian_filter(const sb200_grid_t* gr, void* field, int n
   return 0;
 }
 
+// ---- operators of the reference API that no simulator path uses: Brinkmann
+// penalisation, characteristic function of a level set, vorticity update from a penalised velocity
+// (stencil_ops_3d/brinkmann_penalise_mpi_3d.py:7, char_func_from_level_set_mpi_3d.py:8,
+// update_vorticity_from_velocity_forcing_mpi_3d.py:181-330).  The arithmetic lives in the un-vendored
+// `sopht` package; the published forms are restated (PARITY UNPINNED).
+template <typename T>
+struct BrinkmannOp {
+  T* out;
+  const T* chi;
+  const T* target;
+  const T* f;
+  T lambda;
+  long long n;
+  int ncomp;
+  SB_D void operator()(long long i) const {
+    const T c = lambda * chi[i];
+    for (int k = 0; k < ncomp; ++k)
+      out[i + k * n] = (f[i + k * n] + c * target[i + k * n]) / (T(1) + c);
+  }
+};
+template <typename T>
+struct SineHeavisideOp {
+  T* chi;
+  const T* ls;
+  T bw;
+  SB_D void operator()(long long i) const {
+    const T v = ls[i];
+    T r;
+    if (v > bw)
+      r = T(1);
+    else if (v < -bw)
+      r = T(0);
+    else
+      r = T(0.5) * (T(1) + v / bw + sin(T(M_PI) * v / bw) / T(M_PI));
+    chi[i] = r;
+  }
+};
+template <typename T>
+struct UpdateVorticityPenalisedOp {
+  T* w;
+  const T* up;
+  const T* u;
+  T p;
+  SB_D T d(int c, long long i, const SbGeom& g) const { return up[i + c * g.vol] - u[i + c * g.vol]; }
+  SB_D void operator()(const SbGeom& g, int z, int y, int x) const {
+    if (!g.deep(z, y, x) && !g.written(z, y, x, 1)) return;
+    const long long i = g.idx(z, y, x), sy = g.mx, sz = g.plane;
+    w[i] += p * (d(2, i + sy, g) - d(2, i - sy, g) - d(1, i + sz, g) + d(1, i - sz, g));
+    w[i + g.vol] += p * (d(0, i + sz, g) - d(0, i - sz, g) - d(2, i + 1, g) + d(2, i - 1, g));
+    w[i + 2 * g.vol] += p * (d(1, i + 1, g) - d(1, i - 1, g) - d(0, i + sy, g) + d(0, i - sy, g));
+  }
+};
+extern "C" int sb200_brinkmann_penalise(int dtype, void* penalised, double penalty_factor, const void* char_func,
+                                        const void* penalty_field, const void* field, int ncomp, int64_t count,
+                                        void* stream) {
+  SB_REQUIRE(penalised && char_func && penalty_field && field && ncomp >= 1 && ncomp <= 3,
+             "brinkmann_penalise: bad arguments");
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(count,
+                                                 BrinkmannOp<T>{(T*)penalised, (const T*)char_func,
+                                                                (const T*)penalty_field, (const T*)field,
+                                                                (T)penalty_factor, count, ncomp},
+                                                 stream, "brinkmann_penalise"));
+}
+extern "C" int sb200_char_func_from_level_set(int dtype, void* char_func, const void* level_set, double blend_width,
+                                              int64_t count, void* stream) {
+  SB_REQUIRE(char_func && level_set && blend_width > 0, "char_func_from_level_set: bad arguments");
+  SB_DISPATCH_DTYPE(dtype, return sb_launch_flat(count,
+                                                 SineHeavisideOp<T>{(T*)char_func, (const T*)level_set,
+                                                                    (T)blend_width},
+                                                 stream, "char_func_from_level_set"));
+}
+extern "C" int sb200_update_vorticity_from_penalised_velocity(const sb200_grid_t* gr, void* vorticity,
+                                                              const void* penalised_velocity, const void* velocity,
+                                                              double prefactor, void* stream) {
+  SbGeom g;
+  SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
+  SB_REQUIRE(g.dim == 3 && g.gs >= 1, "update_vorticity_from_penalised_velocity: 3D, ghost_size >= 1");
+  SB_DISPATCH_DTYPE(gr->dtype,
+                    return sb_launch_cells(g,
+                                           UpdateVorticityPenalisedOp<T>{(T*)vorticity, (const T*)penalised_velocity,
+                                                                         (const T*)velocity, (T)prefactor},
+                                           stream, "update_vorticity_penalised"));
+}
+
 // ------------------------------------------------------------- penalise ----
 // Sequential reference semantics (X front/back, then Y, then Z; copy the plane
 // gs+w-1 outwards, then multiply by the sine factor) collapse to

@@ -512,3 +512,71 @@ def gen_laplacian_filter_mpi_kernel_3d(mpi_construct, ghost_exchange_communicato
         _run(vector_field, 3)
     vector_field_filter.kernel_support = kernel_support
     return vector_field_filter
+
+
+# ------------------------------------------------------- operators no simulator path uses
+def gen_brinkmann_penalise_pyst_mpi_kernel_3d(real_t, field_type="scalar"):
+    """reference ``stencil_ops_3d/brinkmann_penalise_mpi_3d.py:7-21``: pointwise (kernel support 0)
+    ``penalised = (field + penalty_factor * char_func * penalty_field) / (1 + penalty_factor * char_func)``"""
+    _check_field_type(field_type)
+    gen_brinkmann_penalise_pyst_mpi_kernel_3d.kernel_support = 0
+    lib = _lib.load()
+    code = _lib.dtype_code(real_t)
+
+    def _run(penalised, penalty_factor, char_func_field, penalty, field, ncomp):
+        st = Staged(_device_of(penalised))
+        out, chi, tgt, f = st(penalised, out=True), st(char_func_field), st(penalty), st(field)
+        _lib.check(lib, lib.sb200_brinkmann_penalise(code, dptr(out), float(penalty_factor), dptr(chi), dptr(tgt),
+                                                     dptr(f), ncomp, chi.numel(), current_stream_ptr()))
+        st.finish()
+
+    if field_type == "scalar":
+        def brinkmann_penalise(penalised_field, penalty_factor, char_func_field, penalty_field, field):
+            _run(penalised_field, penalty_factor, char_func_field, penalty_field, field, 1)
+    else:
+        def brinkmann_penalise(penalised_vector_field, penalty_factor, char_func_field, penalty_vector_field,
+                               vector_field):
+            _run(penalised_vector_field, penalty_factor, char_func_field, penalty_vector_field, vector_field, 3)
+    brinkmann_penalise.kernel_support = 0
+    return brinkmann_penalise
+
+
+def gen_char_func_from_level_set_via_sine_heaviside_pyst_mpi_kernel_3d(blend_width, real_t):
+    """reference ``stencil_ops_3d/char_func_from_level_set_mpi_3d.py:8-30``: 0 below ``-blend_width``, 1 above
+    ``blend_width``, ``0.5 (1 + s + sin(pi s) / pi)`` with ``s = level_set / blend_width`` in between"""
+    gen_char_func_from_level_set_via_sine_heaviside_pyst_mpi_kernel_3d.kernel_support = 0
+    lib = _lib.load()
+    code = _lib.dtype_code(real_t)
+
+    def char_func_from_level_set_via_sine_heaviside(char_func_field, level_set_field):
+        st = Staged(_device_of(char_func_field))
+        chi, ls = st(char_func_field, out=True), st(level_set_field)
+        _lib.check(lib, lib.sb200_char_func_from_level_set(code, dptr(chi), dptr(ls), float(blend_width),
+                                                           chi.numel(), current_stream_ptr()))
+        st.finish()
+    char_func_from_level_set_via_sine_heaviside.kernel_support = 0
+    return char_func_from_level_set_via_sine_heaviside
+
+
+def gen_update_vorticity_from_penalised_velocity_pyst_mpi_kernel_3d(real_t, mpi_construct,
+                                                                    ghost_exchange_communicator):
+    """reference ``update_vorticity_from_velocity_forcing_mpi_3d.py:181-330``:
+    ``vorticity += prefactor * curl(penalised_velocity - velocity)`` on the cells the wrapper writes"""
+    kernel_support = 1
+    gen_update_vorticity_from_penalised_velocity_pyst_mpi_kernel_3d.kernel_support = kernel_support
+    check_valid_ghost_size_and_kernel_support(
+        ghost_size=ghost_exchange_communicator.ghost_size, kernel_support=kernel_support)
+    ctx = OpContext(real_t, mpi_construct, ghost_exchange_communicator)
+
+    def update_vorticity_from_penalised_velocity(vorticity_field, penalised_velocity_field, velocity_field,
+                                                 prefactor):
+        st = ctx.stage()
+        w = st(vorticity_field, out=True)
+        up, u = st(penalised_velocity_field, out=ctx.distributed), st(velocity_field, out=ctx.distributed)
+        ctx.exchange_vector(u)
+        ctx.exchange_vector(up)
+        ctx.call("sb200_update_vorticity_from_penalised_velocity", ctx.gref, dptr(w), dptr(up), dptr(u),
+                 float(prefactor), ctx.stream())
+        st.finish()
+    update_vorticity_from_penalised_velocity.kernel_support = kernel_support
+    return update_vorticity_from_penalised_velocity

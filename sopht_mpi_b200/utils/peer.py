@@ -78,12 +78,12 @@ class PeerExchange:
         self._peer_dev = [self.peer[q][0].device.index for q in range(self.nranks)]
         for q in range(self.nranks):
             if q != self.rank:
-                # this device -> peer: the push kernel stores through the mapped pointers
+                # both directions (torch maps the imported buffers in a context on the exporting device,
+                # so that context exists in this process anyway): without the reverse mapping the driver
+                # stages copies through the host (25 GB/s instead of ~640 GB/s,
+                # profiles/r01_peer_copy.txt)
                 _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._dev, self._peer_dev[q]))
-                if self.transport == "copy":
-                    # copy engines: without the reverse mapping the driver stages the copy through the
-                    # host (25 GB/s instead of ~640 GB/s, profiles/r01_peer_copy.txt)
-                    _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._peer_dev[q], self._dev))
+                _lib.check(self._lib, self._lib.sb200_enable_peer_access(self._peer_dev[q], self._dev))
 
     @property
     def mode(self):

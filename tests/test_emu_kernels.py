@@ -596,3 +596,31 @@ def test_one_pass_order1_multiplicative_filter(setup3d):
     out2, a1, b1 = np.empty_like(w2), np.zeros(shape2, real_t), np.zeros(shape2, real_t)
     call("sb200_laplacian_filter_order1_out_of_place", ctypes.byref(g2), ptr(out2), ptr(w2), 3, ptr(a1), ptr(b1), None)
     assert np.array_equal(out2, ref2) and np.array_equal(a1, a)
+
+
+def test_operators_outside_the_simulator_paths(setup3d):
+    """Brinkmann penalisation, level set -> characteristic function, vorticity update from a penalised
+    velocity against their closed forms / the velocity-forcing update of the difference."""
+    real_t, rng, n, gs, shape, g = setup3d
+    code = _lib.dtype_code(real_t)
+    cells = int(np.prod(shape))
+    f = rng.uniform(size=(3,) + shape).astype(real_t)
+    tgt = rng.uniform(size=(3,) + shape).astype(real_t)
+    chi = rng.uniform(size=shape).astype(real_t)
+    out = np.zeros_like(f)
+    call("sb200_brinkmann_penalise", code, ptr(out), 7.5, ptr(chi), ptr(tgt), ptr(f), 3, cells, None)
+    lam = real_t(7.5)
+    assert _rel(out, (f + lam * chi * tgt) / (1 + lam * chi)) < _tol(real_t)
+    ls = (rng.uniform(size=shape) - 0.5).astype(real_t)
+    got = np.zeros_like(ls)
+    call("sb200_char_func_from_level_set", code, ptr(got), ptr(ls), 0.2, cells, None)
+    s = ls / real_t(0.2)
+    want = np.where(ls > 0.2, 1.0, np.where(ls < -0.2, 0.0, 0.5 * (1 + s + np.sin(np.pi * s) / np.pi)))
+    assert np.abs(got - want).max() < (1e-6 if real_t == np.float32 else 1e-14)
+    assert got.min() >= -1e-6 and got.max() <= 1 + 1e-6
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    up, u = tgt, f
+    ref = w.copy()
+    st.update_vorticity_from_velocity_forcing_mpi(ref, (up - u).astype(real_t), 0.4, gs)
+    call("sb200_update_vorticity_from_penalised_velocity", ctypes.byref(g), ptr(w), ptr(up), ptr(u), 0.4, None)
+    assert _rel(w, ref) < _tol(real_t)

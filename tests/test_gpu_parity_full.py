@@ -595,3 +595,60 @@ def test_virtual_boundary_forcing_host_mirrors_follow_the_device(cuda):
     torch.cuda.synchronize()
     with pytest.raises(RuntimeError):
         vbf.compute_interaction_force_on_lag_grid(u, pos, vel)
+
+
+def test_flow_past_sphere_example_with_the_in_repo_forcing_grid(cuda):
+    """The call sequence of examples/3d_examples/FlowPastSphereCase/flow_past_sphere_case.py:32-140
+    (RigidBodyFlowInteractionMPI + SphereForcingGrid + navier_stokes_with_forcing), at 64x32x32, against
+    the composed oracle; the sphere is at rest, so its kinematics are uploaded once."""
+    import types
+
+    from sopht_mpi_b200.simulator import RigidBodyFlowInteractionMPI, SphereForcingGrid, UnboundedFlowSimulator3D
+
+    real_t, n, x_range = np.float32, (32, 32, 64), 1.0
+    kw = dict(grid_size=n, x_range=x_range, kinematic_viscosity=2e-3, flow_type="navier_stokes_with_forcing",
+              real_t=real_t, with_free_stream_flow=True)
+    sim = UnboundedFlowSimulator3D(**kw)
+    ora = FlowSimulatorOracle3D(**kw)
+    diameter = 0.4 * min(n[0], n[1]) / n[2]
+    sphere = types.SimpleNamespace(
+        radius=diameter / 2, position_collection=np.array([[0.25], [0.5 * sim.y_range], [0.5 * sim.z_range]]),
+        velocity_collection=np.zeros((3, 1)), omega_collection=np.zeros((3, 1)),
+        director_collection=np.eye(3).reshape(3, 3, 1))
+    interactor = RigidBodyFlowInteractionMPI(
+        mpi_construct=sim.mpi_construct, mpi_ghost_exchange_communicator=sim.mpi_ghost_exchange_communicator,
+        rigid_body=sphere, eul_grid_forcing_field=sim.eul_grid_forcing_field,
+        eul_grid_velocity_field=sim.velocity_field, virtual_boundary_stiffness_coeff=-6e5 / 4,
+        virtual_boundary_damping_coeff=-3.5e2 / 4, dx=sim.dx, grid_dim=3, master_rank=0,
+        forcing_grid_cls=SphereForcingGrid,
+        num_forcing_points_along_equator=int(1.875 * diameter / x_range * n[2]))
+    grid = interactor.forcing_grid
+    assert isinstance(grid, SphereForcingGrid) and grid.num_lag_nodes > 100
+    area = grid.get_maximum_lagrangian_grid_spacing() ** 2
+    vbf_o = ib_oracle.VirtualBoundaryForcingOracle(-6e5 / 4 * area, -3.5e2 / 4 * area, 3, ora.dx, real_t, np.float64,
+                                                   sim.ghost_size)
+    u_inf = [1.0, 0.0, 0.0]
+    ora.compute_flow_velocity(u_inf)
+    sim.compute_flow_velocity(free_stream_velocity=u_inf)
+    uploads = []
+    real_upload = interactor._upload_kinematics
+    interactor._upload_kinematics = lambda p, v: (uploads.append(interactor._kin_i), real_upload(p, v))[1]
+    for _ in range(4):
+        dt = ora.compute_stable_timestep(dt_prefac=0.5)
+        assert abs(sim.compute_stable_timestep(dt_prefac=0.5) - dt) <= 1e-5 * dt
+        vbf_o.compute_interaction_force_on_eul_and_lag_grid(ora.eul_grid_forcing_field, ora.velocity_field,
+                                                            grid.position_field, grid.velocity_field)
+        interactor()
+        vbf_o.time_step(dt)
+        interactor.time_step(dt)
+        ora.time_step(dt, free_stream_velocity=u_inf)
+        sim.time_step(dt=dt, free_stream_velocity=u_inf)
+    assert len(set(uploads[1:])) == 1  # the device copy of the kinematics was reused after the first upload
+    tol = TOL[real_t]
+    assert _rel(sim.vorticity_field, ora.vorticity_field) <= tol
+    assert _rel(sim.velocity_field, ora.velocity_field) <= tol
+    interactor.compute_flow_forces_and_torques()
+    vbf_o.compute_interaction_force_on_lag_grid(ora.velocity_field, grid.position_field, grid.velocity_field)
+    assert _rel(interactor.global_lag_grid_forcing_field, vbf_o.forcing) <= 1e-4
+    assert interactor.body_flow_forces[0, 0] > 0  # drag along the free stream
+    assert np.allclose(interactor.body_flow_forces[:, 0], -vbf_o.forcing.sum(axis=1), rtol=1e-3, atol=1e-9)
