@@ -161,6 +161,14 @@ int sb200_vorticity_rhs_fused_3d(const sb200_grid_t* g, void* out, const void* v
                                  const void* velocity, const void* forcing, double curl_prefactor,
                                  double nu_dt_by_dx2, void* stream);
 
+/* The same sweep restricted to the output planes [z_begin, z_end) (it reads the input planes z_begin - 2
+ * ... z_end + 1): lets the caller run the planes that do not depend on ghost planes while the halo
+ * exchange is in flight, and the remaining ones afterwards (the reference's interior -> Waitall ->
+ * boundary slabs structure, e.g. stencil_ops_3d/curl_mpi_3d.py:41-194). */
+int sb200_vorticity_rhs_fused_3d_range(const sb200_grid_t* g, void* out, const void* vorticity,
+                                       const void* velocity, double curl_prefactor, double nu_dt_by_dx2,
+                                       int z_begin, int z_end, void* stream);
+
 /* ---- unbounded Poisson solver ---------------------------------------------
  * poisson_solver_3d/UnboundedPoissonSolverMPI3D.py:22-187 (+ fft_mpi_3d.py),
  * poisson_solver_2d/UnboundedPoissonSolverMPI2D.py:12-153.

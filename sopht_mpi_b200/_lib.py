@@ -79,6 +79,7 @@ PROTOTYPES = {
     "sb200_velocity_from_stream_function": (
         c_int, [_G, _V, _V, c_double, POINTER(c_double), _V, _V, _V]),
     "sb200_vorticity_rhs_fused_3d": (c_int, [_G, _V, _V, _V, _V, c_double, c_double, _V]),
+    "sb200_vorticity_rhs_fused_3d_range": (c_int, [_G, _V, _V, _V, c_double, c_double, c_int, c_int, _V]),
     "sb200_poisson_create": (
         c_int, [POINTER(_V), c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_int, c_int, _V]),
     "sb200_poisson_destroy": (c_int, [_V]),

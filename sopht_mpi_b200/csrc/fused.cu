@@ -48,7 +48,7 @@ SB_D int sb_yx_mask(const SbGeom& g, int y, int x) {
 template <typename T, int TY, int TX, int NT>
 __global__ void __launch_bounds__(NT)
     sb_vorticity_fused_kernel(SbGeom g, T* __restrict__ out, const T* __restrict__ w, const T* __restrict__ u,
-                              T p, T d, int zchunk) {
+                              T p, T d, int zchunk, int z_begin, int z_end) {
   using FT = FusedTile<TY, TX, NT>;
   SB_DYN_SMEM(smem_raw);
   T* sbuf = reinterpret_cast<T*>(smem_raw);  // [3][3][R2]
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(NT)
   T* sw2 = sw1 + 6 * FT::R1;                 // [3][3][R1]
   const int tid = threadIdx.x;
   const int y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
-  const int zb = blockIdx.z * zchunk;
-  const int ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
+  const int zb = z_begin + blockIdx.z * zchunk;
+  const int ze = zb + zchunk < z_end ? zb + zchunk : z_end;
   const long long vol = g.vol, plane = g.plane;
   const int zlo = g.phys[0] ? g.gs : 1, zhi = g.phys[1] ? g.mz - g.gs : g.mz - 1;
   const int zring_lo = g.phys[0] ? g.gs + 1 : 0, zring_hi = g.phys[1] ? g.mz - g.gs - 1 : g.mz;
@@ -231,13 +231,14 @@ SB_D void sb_st2(float* p, F2 v) { *reinterpret_cast<F2*>(p) = v; }
 
 template <int R, bool FAST>
 SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, const float* __restrict__ w,
-                                     const float* __restrict__ u, float p, float d, int zchunk, float* smem) {
+                                     const float* __restrict__ u, float p, float d, int zchunk, int z_begin,
+                                     int z_end, float* smem) {
   using FV = FusedV2<R>;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
   const int x = (int)blockIdx.x * FV::TXU - 2 + 2 * lane;  // first cell of the strip (even)
   const int y = (int)blockIdx.y * FV::TYU - 2 + row;
-  const int zb = blockIdx.z * zchunk;
-  const int ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
+  const int zb = z_begin + blockIdx.z * zchunk;
+  const int ze = zb + zchunk < z_end ? zb + zchunk : z_end;
   const long long vol = g.vol, plane = g.plane;
   const int zlo = g.phys[0] ? g.gs : 1, zhi = g.phys[1] ? g.mz - g.gs : g.mz - 1;
   const int zring_lo = g.phys[0] ? g.gs + 1 : 0, zring_hi = g.phys[1] ? g.mz - g.gs - 1 : g.mz;
@@ -405,7 +406,8 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
 template <int R>
 __global__ void __launch_bounds__(32 * R)
     sb_vorticity_fused_v2_kernel(SbGeom g, float* __restrict__ out, const float* __restrict__ w,
-                                 const float* __restrict__ u, float p, float d, int zchunk) {
+                                 const float* __restrict__ u, float p, float d, int zchunk, int z_begin,
+                                 int z_end) {
   using FV = FusedV2<R>;
   SB_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -415,14 +417,14 @@ __global__ void __launch_bounds__(32 * R)
   const bool fast = x0 - 1 >= g.gs + 1 && x0 + FV::TXU <= g.mx - g.gs - 2 && y0 - 1 >= g.gs + 1 &&
                     y0 + FV::TYU <= g.my - g.gs - 2 && x0 + 62 <= g.mx && y0 + R - 2 <= g.my;
   if (fast)
-    sb_vorticity_fused_v2_body<R, true>(g, out, w, u, p, d, zchunk, smem);
+    sb_vorticity_fused_v2_body<R, true>(g, out, w, u, p, d, zchunk, z_begin, z_end, smem);
   else
-    sb_vorticity_fused_v2_body<R, false>(g, out, w, u, p, d, zchunk, smem);
+    sb_vorticity_fused_v2_body<R, false>(g, out, w, u, p, d, zchunk, z_begin, z_end, smem);
 }
 
 template <int R>
 static int launch_fused_v2(const SbGeom& g, void* out, const void* w, const void* u, double p, double d,
-                           void* stream) {
+                           int z0, int z1, void* stream) {
   using FV = FusedV2<R>;
   const size_t smem = sizeof(float) * FV::ELEMS;
   const unsigned gx = (g.mx + FV::TXU - 1) / FV::TXU, gy = (g.my + FV::TYU - 1) / FV::TYU;
@@ -441,14 +443,15 @@ static int launch_fused_v2(const SbGeom& g, void* out, const void* w, const void
     resident = cached;
   }
 #endif
-  int chunks = 1, zchunk = g.mz;
+  const int nzr = z1 - z0;  // planes to produce
+  int chunks = 1, zchunk = nzr;
   {
     long long best = -1;
     const long long tiles = (long long)gx * gy;
-    for (int c = 1; c <= g.mz; ++c) {
-      const int zc = (g.mz + c - 1) / c;
+    for (int c = 1; c <= nzr; ++c) {
+      const int zc = (nzr + c - 1) / c;
       if (zc < 8 && c > 1) break;
-      const int cc = (g.mz + zc - 1) / zc;
+      const int cc = (nzr + zc - 1) / zc;
       const long long waves = (tiles * cc + resident - 1) / resident;
       const long long cost = waves * (zc + 4);
       if (best < 0 || cost < best) {
@@ -459,14 +462,14 @@ static int launch_fused_v2(const SbGeom& g, void* out, const void* w, const void
     }
   }
   SB_LAUNCH_COOP((sb_vorticity_fused_v2_kernel<R>), dim3(gx, gy, (unsigned)chunks), dim3(FV::NT), smem, stream, g,
-                 (float*)out, (const float*)w, (const float*)u, (float)p, (float)d, zchunk);
+                 (float*)out, (const float*)w, (const float*)u, (float)p, (float)d, zchunk, z0, z1);
   SB_CHECK_LAUNCH("vorticity_fused_v2");
   return 0;
 }
 
 template <typename T, int TY, int TX, int NT>
 static int launch_fused(const SbGeom& g, void* out, const void* w, const void* u, double p, double d,
-                        void* stream) {
+                        int z0, int z1, void* stream) {
   using FT = FusedTile<TY, TX, NT>;
   const size_t smem = sizeof(T) * FT::ELEMS;
   const unsigned gx = (g.mx + TX - 1) / TX, gy = (g.my + TY - 1) / TY;
@@ -488,14 +491,15 @@ static int launch_fused(const SbGeom& g, void* out, const void* w, const void* u
     resident = cached;
   }
 #endif
-  int chunks = 1, zchunk = g.mz;
+  const int nzr = z1 - z0;  // planes to produce
+  int chunks = 1, zchunk = nzr;
   {
     long long best = -1;
     const long long tiles = (long long)gx * gy;
-    for (int c = 1; c <= g.mz; ++c) {
-      const int zc = (g.mz + c - 1) / c;
+    for (int c = 1; c <= nzr; ++c) {
+      const int zc = (nzr + c - 1) / c;
       if (zc < 8 && c > 1) break;
-      const int cc = (g.mz + zc - 1) / zc;  // chunks actually needed for this chunk length
+      const int cc = (nzr + zc - 1) / zc;  // chunks actually needed for this chunk length
       const long long waves = (tiles * cc + resident - 1) / resident;
       const long long cost = waves * (zc + 4);
       if (best < 0 || cost < best) {
@@ -506,35 +510,47 @@ static int launch_fused(const SbGeom& g, void* out, const void* w, const void* u
     }
   }
   SB_LAUNCH_COOP((sb_vorticity_fused_kernel<T, TY, TX, NT>), dim3(gx, gy, (unsigned)chunks), dim3(NT), smem,
-                 stream, g, (T*)out, (const T*)w, (const T*)u, (T)p, (T)d, zchunk);
+                 stream, g, (T*)out, (const T*)w, (const T*)u, (T)p, (T)d, zchunk, z0, z1);
   SB_CHECK_LAUNCH("vorticity_fused");
   return 0;
 }
 
-extern "C" int sb200_vorticity_rhs_fused_3d(const sb200_grid_t* gr, void* out, const void* vorticity,
-                                            const void* velocity, const void* forcing,
-                                            double curl_prefactor, double nu_dt_by_dx2, void* stream) {
+extern "C" int sb200_vorticity_rhs_fused_3d_range(const sb200_grid_t* gr, void* out, const void* vorticity,
+                                                  const void* velocity, double curl_prefactor, double nu_dt_by_dx2,
+                                                  int z_begin, int z_end, void* stream) {
   SbGeom g;
   SB_REQUIRE(sb_make_geom(gr, &g) == 0, "bad grid");
   SB_REQUIRE(g.dim == 3, "vorticity_rhs_fused_3d: 3D only");
   SB_REQUIRE(g.gs >= 2, "vorticity_rhs_fused_3d needs ghost_size >= 2");
   SB_REQUIRE(out && vorticity && velocity && out != vorticity, "vorticity_rhs_fused_3d: bad pointers");
-  SB_REQUIRE(forcing == nullptr,
-             "vorticity_rhs_fused_3d: apply the forcing update first "
-             "(sb200_update_vorticity_from_velocity_forcing)");
   SB_REQUIRE(g.plane < (1LL << 31), "vorticity_rhs_fused_3d: plane too large");
-  // 16 x 32 tiles, 256 threads: (20 x 36) and (18 x 34) staged cells fill 3 passes of the block almost
-  // completely (94 % / 80 %) and the halo overhead is 1.41x; measured 262 us at 256^3 against 363 us
-  // for 8 x 64 (and 278-417 us for 12x32, 24x32, 16x48, 16x16, 512 or 128 threads)
+  SB_REQUIRE(z_begin >= 0 && z_end <= g.mz, "vorticity_rhs_fused_3d: bad plane range");
+  if (z_end <= z_begin) return 0;
   if (gr->dtype == SB200_F32) {
     // version 2 needs even row lengths (8-byte strips); SB200_FUSED_V2 = 0 / rows selects for measurements
     static const int v2 = getenv("SB200_FUSED_V2") ? atoi(getenv("SB200_FUSED_V2")) : 24;
     if (v2 > 0 && (g.mx & 1) == 0) {
-      if (v2 == 16) return launch_fused_v2<16>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
-      if (v2 == 20) return launch_fused_v2<20>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
-      return launch_fused_v2<24>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+      if (v2 == 16)
+        return launch_fused_v2<16>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, z_begin, z_end, stream);
+      if (v2 == 20)
+        return launch_fused_v2<20>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, z_begin, z_end, stream);
+      return launch_fused_v2<24>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, z_begin, z_end, stream);
     }
-    return launch_fused<float, 16, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+    // 16 x 32 tiles, 256 threads (version 1): measured best of 8x64, 12x32, 24x32, 16x48, 16x16 in round 1
+    return launch_fused<float, 16, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, z_begin, z_end,
+                                            stream);
   }
-  return launch_fused<double, 8, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, stream);
+  return launch_fused<double, 8, 32, 256>(g, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, z_begin, z_end,
+                                          stream);
+}
+
+extern "C" int sb200_vorticity_rhs_fused_3d(const sb200_grid_t* gr, void* out, const void* vorticity,
+                                            const void* velocity, const void* forcing,
+                                            double curl_prefactor, double nu_dt_by_dx2, void* stream) {
+  SB_REQUIRE(gr, "bad grid");
+  SB_REQUIRE(forcing == nullptr,
+             "vorticity_rhs_fused_3d: apply the forcing update first "
+             "(sb200_update_vorticity_from_sparse_forcing)");
+  return sb200_vorticity_rhs_fused_3d_range(gr, out, vorticity, velocity, curl_prefactor, nu_dt_by_dx2, 0,
+                                            gr->n[0] + 2 * gr->gs, stream);
 }

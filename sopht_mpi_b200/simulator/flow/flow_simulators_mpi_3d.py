@@ -377,18 +377,33 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
         w, u = self.vorticity_field.tensor, self.velocity_field.tensor
         if self._vorticity_alt is None:
             self._vorticity_alt = torch.empty_like(w)
-        if ctx.distributed:
-            # ghost planes of omega and u stand in for the reference's exchanges of u x omega
-            # and of omega between its three sweeps
-            ctx.exchange_vector(w)
-            # (the interactor has usually just exchanged the velocity: its ghost planes are current)
-            if not self.mpi_ghost_exchange_communicator.is_fresh(self.velocity_field):
-                self.mpi_ghost_exchange_communicator.exchange_vector_field_init(self.velocity_field)
-                self.mpi_ghost_exchange_communicator.exchange_finalise()
         alt = self._vorticity_alt
-        ctx.call("sb200_vorticity_rhs_fused_3d", ctx.gref, dptr(alt), dptr(w), dptr(u), None,
-                 float(self.real_t(dt / (2 * self.dx))),
-                 float(self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx)), ctx.stream())
+        p = float(self.real_t(dt / (2 * self.dx)))
+        d = float(self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx))
+        mz = int(w.shape[1])
+        lo, hi = 0, mz
+        comm = self.mpi_ghost_exchange_communicator
+        if ctx.distributed:
+            # ghost planes of omega and u stand in for the reference's exchanges of u x omega and of omega
+            # between its three sweeps.  The exchange is started, the output planes that do not read a
+            # ghost plane (the sweep reaches two planes up and down) run while it is in flight, the
+            # planes next to the slab faces follow once it has landed.
+            comm.exchange_vector_field_init(self.vorticity_field)
+            # (the interactor has usually just exchanged the velocity: its ghost planes are current)
+            if not comm.is_fresh(self.velocity_field):
+                comm.exchange_vector_field_init(self.velocity_field)
+            reach = 2 + self.ghost_size
+            faces = self.mpi_construct.physical_faces
+            lo = 0 if faces[0] else reach
+            hi = mz if faces[1] else mz - reach
+        ctx.call("sb200_vorticity_rhs_fused_3d_range", ctx.gref, dptr(alt), dptr(w), dptr(u), p, d, lo, hi,
+                 ctx.stream())
+        if ctx.distributed:
+            comm.exchange_finalise()
+            for z0, z1 in ((0, lo), (hi, mz)):
+                if z1 > z0:
+                    ctx.call("sb200_vorticity_rhs_fused_3d_range", ctx.gref, dptr(alt), dptr(w), dptr(u), p, d, z0, z1,
+                             ctx.stream())
         w.data, alt.data = alt.data, w.data
 
     def navier_stokes_with_forcing_timestep(self, dt, free_stream_velocity=None):

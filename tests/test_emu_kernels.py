@@ -624,3 +624,22 @@ def test_operators_outside_the_simulator_paths(setup3d):
     st.update_vorticity_from_velocity_forcing_mpi(ref, (up - u).astype(real_t), 0.4, gs)
     call("sb200_update_vorticity_from_penalised_velocity", ctypes.byref(g), ptr(w), ptr(up), ptr(u), 0.4, None)
     assert _rel(w, ref) < _tol(real_t)
+
+
+@pytest.mark.parametrize("real_t", [np.float64, np.float32], ids=["f64", "f32"])
+def test_fused_vorticity_update_by_plane_ranges(real_t):
+    """The plane-range entry point (interior planes while the halo exchange is in flight, the planes next
+    to the slab faces afterwards) assembles exactly the whole-grid result."""
+    rng = np.random.default_rng(3)
+    gs, n = 2, (20, 10, 66)
+    shape = tuple(v + 2 * gs for v in n)
+    g = _lib.make_grid(3, real_t, gs, n, (0, 0, 1, 1, 1, 1))  # an inner z-slab
+    w = rng.uniform(size=(3,) + shape).astype(real_t)
+    u = (rng.uniform(size=(3,) + shape) - 0.5).astype(real_t)
+    whole = np.full_like(w, np.nan)
+    call("sb200_vorticity_rhs_fused_3d", ctypes.byref(g), ptr(whole), ptr(w), ptr(u), None, 0.3, 0.05, None)
+    parts = np.full_like(w, np.nan)
+    mz = shape[0]
+    for z0, z1 in ((4, mz - 4), (0, 4), (mz - 4, mz)):
+        call("sb200_vorticity_rhs_fused_3d_range", ctypes.byref(g), ptr(parts), ptr(w), ptr(u), 0.3, 0.05, z0, z1, None)
+    assert not np.isnan(parts).any() and np.array_equal(parts, whole)
