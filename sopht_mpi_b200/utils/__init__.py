@@ -8,3 +8,4 @@ from .mpi_utils_2d import (MPIConstruct2D, MPIGhostCommunicator2D, MPIFieldCommu
                            MPILagrangianFieldCommunicator2D)
 from .mpi_utils_3d import (MPIConstruct3D, MPIGhostCommunicator3D, MPIFieldCommunicator3D,
                            MPILagrangianFieldCommunicator3D)
+from .mpi_io import MPIIO
