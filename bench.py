@@ -636,6 +636,7 @@ def main():
         # release the CUDA-IPC mappings of the other ranks' exchange buffers before any rank exits
         import gc
 
+        solver.close()
         del solver, sim, interactor
         gc.collect()
         torch.cuda.ipc_collect()

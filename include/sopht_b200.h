@@ -226,6 +226,14 @@ int sb200_peer_copy_blocks(int n, void* const* dst, const int* dst_device, const
 int sb200_peer_push_blocks(int n, void* const* dst, const void* const* src, int64_t bytes, int blocks_per_peer,
                            void* const* signal_flags, int epoch, void* done_counters, void* stream);
 int sb200_peer_wait_flags(const void* flags, int n, int epoch, void* error_flag, void* stream);
+/* Exchange buffers shared between the ranks of a node: plain device allocations (zero-initialised) whose
+ * CUDA IPC handle (64 bytes) another process opens while its own device is current, so that its kernels
+ * can store through the mapping over NVLink (cudaIpcMemLazyEnablePeerAccess). */
+int sb200_peer_alloc(int64_t bytes, void** ptr_out);
+int sb200_peer_free(void* ptr);
+int sb200_ipc_export(const void* ptr, void* handle_out_64);
+int sb200_ipc_open(const void* handle_64, void** ptr_out);
+int sb200_ipc_close(void* ptr);
 /* 1 when the pruned in-kernel FFT backend (backend = 1, power-of-two grids) is built in */
 int sb200_poisson_fft_available(void);
 

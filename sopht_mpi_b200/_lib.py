@@ -91,6 +91,11 @@ PROTOTYPES = {
     "sb200_peer_copy_blocks": (c_int, [c_int, _V, _V, _V, c_int, c_int64, _V]),
     "sb200_peer_push_blocks": (c_int, [c_int, _V, _V, c_int64, c_int, _V, c_int, _V, _V]),
     "sb200_peer_wait_flags": (c_int, [_V, c_int, c_int, _V, _V]),
+    "sb200_peer_alloc": (c_int, [c_int64, POINTER(_V)]),
+    "sb200_peer_free": (c_int, [_V]),
+    "sb200_ipc_export": (c_int, [_V, _V]),
+    "sb200_ipc_open": (c_int, [_V, POINTER(_V)]),
+    "sb200_ipc_close": (c_int, [_V]),
     "sb200_poisson_set_profiling": (c_int, [_V, c_int]),
     "sb200_poisson_last_stage_ms": (c_int, [_V, _V, c_int]),
     "sb200_poisson_slab_buffer_bytes": (c_int64, [_V, c_int]),

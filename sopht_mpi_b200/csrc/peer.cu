@@ -4,6 +4,9 @@
 // once peer access is enabled between the two devices.
 #include "sb200_common.h"
 
+#include <cstdlib>
+#include <cstring>
+
 extern "C" int sb200_enable_peer_access(int device, int peer_device) {
 #ifndef SB200_EMU
   if (device == peer_device) return 0;
@@ -147,5 +150,76 @@ extern "C" int sb200_peer_wait_flags(const void* flags, int n, int epoch, void* 
   SB_REQUIRE(flags && error_flag && n >= 1 && n <= 32, "peer_wait_flags: bad arguments");
   SB_LAUNCH(sb_wait_flags_kernel, dim3(1), dim3(32), 0, stream, (const int*)flags, n, epoch, (int*)error_flag);
   SB_CHECK_LAUNCH("peer_wait_flags");
+  return 0;
+}
+
+// ---- exchange buffers with our own CUDA IPC mapping.  The buffers are plain cudaMalloc allocations
+// (so the pointer IS the base the handle refers to); a peer opens the handle while ITS OWN device is
+// current, with cudaIpcMemLazyEnablePeerAccess: the mapping lives in the peer's compute context and its
+// kernels can store through it over NVLink.  (torch's tensor sharing maps imported storages in a
+// context on the EXPORTING device instead, which kernel stores from the importing device fault on.)
+extern "C" int sb200_peer_alloc(int64_t bytes, void** ptr_out) {
+  SB_REQUIRE(ptr_out && bytes > 0, "peer_alloc: bad arguments");
+#ifndef SB200_EMU
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  if (e != cudaSuccess) {
+    sb_set_error("peer_alloc: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  *ptr_out = p;
+#else
+  *ptr_out = calloc(1, (size_t)bytes);
+#endif
+  return 0;
+}
+extern "C" int sb200_peer_free(void* ptr) {
+#ifndef SB200_EMU
+  if (ptr) cudaFree(ptr);
+#else
+  free(ptr);
+#endif
+  return 0;
+}
+extern "C" int sb200_ipc_export(const void* ptr, void* handle_out_64) {
+  SB_REQUIRE(ptr && handle_out_64, "ipc_export: bad arguments");
+#ifndef SB200_EMU
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+  if (e != cudaSuccess) {
+    sb_set_error("ipc_export: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  memcpy(handle_out_64, &h, 64);
+#else
+  memset(handle_out_64, 0, 64);
+#endif
+  return 0;
+}
+extern "C" int sb200_ipc_open(const void* handle_64, void** ptr_out) {
+  SB_REQUIRE(handle_64 && ptr_out, "ipc_open: bad arguments");
+#ifndef SB200_EMU
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, 64);
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    sb_set_error("ipc_open: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  *ptr_out = p;
+#else
+  *ptr_out = nullptr;
+#endif
+  return 0;
+}
+extern "C" int sb200_ipc_close(void* ptr) {
+#ifndef SB200_EMU
+  if (ptr) cudaIpcCloseMemHandle(ptr);
+#else
+  (void)ptr;
+#endif
   return 0;
 }

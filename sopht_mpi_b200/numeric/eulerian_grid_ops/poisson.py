@@ -70,6 +70,15 @@ class _UnboundedPoissonSolver:
         except Exception:
             pass
 
+    def close(self):
+        """Release the exchange buffers shared with the other ranks (collective: call it on every rank
+        before the process group goes away)."""
+        peer = getattr(self, "_peer", None)
+        if peer is not None:
+            peer.close(collective=True)
+            self._peer = None
+            self._slab_bufs = []
+
     @property
     def workspace_bytes(self):
         return int(self.lib.sb200_poisson_workspace_bytes(self._handle))

@@ -45,6 +45,8 @@ def main():
         inner = (slice(None), slice(gs, -gs), slice(gs, -gs), slice(gs, -gs))
         err = rel(np.asarray(out)[inner], ref[:, rank * nzl + gs:rank * nzl + gs + nzl, gs:-gs, gs:-gs])
         assert err <= tol, ("poisson", real_t, err)
+        getattr(solver, "_peer", None) and solver._peer.check()
+        solver.close()
 
         # ---------------- full simulator steps on slabs vs single-domain oracle
         n = (32, 16, 32)
@@ -84,6 +86,7 @@ def main():
             assert err <= tol, (name, real_t, err)
         gmax = sim.get_max_vorticity()
         assert abs(gmax - ora.vorticity_field[:, gs:-gs, gs:-gs, gs:-gs].max()) <= 50 * tol
+        sim.unbounded_poisson_solver.close()
 
     # ---------------- virtual boundary forcing across slabs: ownership, forces, spreading + ghost sum
     from sopht_mpi_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcingMPI
@@ -148,6 +151,9 @@ def main():
     check_replicated_solves(gs)
 
     dist.barrier()
+    import gc
+
+    gc.collect()
     if rank == 0:
         print("DIST_GPU_WORKER_OK")
     dist.destroy_process_group()
