@@ -258,9 +258,8 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
   float* sA = smem;  // [parity][array][row + 1][64]
   const int soff = (row + 1) * FV::ROW + 2 * lane;
 
-  F2 wp[3] = {}, b1[3] = {}, b2xy[2] = {}, q2[3] = {}, q3[3] = {};
   // zero the guard rows once (rows 0 and R + 1 of every array are only read by the edge rows, whose
-  // results are never stored, but they must not hold NaN patterns that trap nothing: keep them finite)
+  // results are never stored; keep them finite)
   for (int i = threadIdx.x; i < FV::ELEMS; i += FV::NT) smem[i] = 0.f;
   __syncthreads();
 
@@ -295,29 +294,25 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
       }
     }
   };
-  F2 wn[3], un[3];
-  load_plane(zb - 2, wn, un);
-
-  for (int zf = zb - 2; zf <= ze + 1; ++zf) {
+  // One plane of the march.  The z history lives in registers that ROTATE through the roles (the
+  // march is unrolled six times below, the period of the 3-deep omega / buf / omega2 and the 2-deep u
+  // rotations), so no register is ever copied:
+  //   wnext/unext: plane zf + 1 (loads in flight)   wcur/ucur: plane zf   wprev: plane zf - 1
+  //   b0 = buf(zf) (written here), b1 = buf(zf - 1), b2 = buf(zf - 2)
+  //   q1 = omega2(zf - 1) (written here), q2 = omega2(zf - 2), q3 = omega2(zf - 3)
+  auto step = [&](int zf, F2 (&wnext)[3], F2 (&unext)[3], const F2 (&wc)[3], const F2 (&uc)[3], const F2 (&wp)[3],
+                  F2 (&b0)[3], const F2 (&b1)[3], const F2 (&b2)[3], F2 (&q1)[3], const F2 (&q2)[3],
+                  const F2 (&q3)[3]) {
     const int par = zf & 1;
     float* sw = sA + par * 5 * FV::ARR;               // written this iteration
     const float* sr = sA + (par ^ 1) * 5 * FV::ARR;   // written by the previous iteration
-    // ---- plane zf: omega, u (loaded one iteration ahead) -> u x omega; start the loads of plane zf + 1
-    F2 wc[3], uc[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      wc[c] = wn[c];
-      uc[c] = un[c];
-    }
-    if (zf + 1 <= ze + 1) load_plane(zf + 1, wn, un);
-    F2 b0[3];
+    if (zf + 1 <= ze + 1) load_plane(zf + 1, wnext, unext);
     b0[0] = F2{uc[1].x * wc[2].x - uc[2].x * wc[1].x, uc[1].y * wc[2].y - uc[2].y * wc[1].y};
     b0[1] = F2{uc[2].x * wc[0].x - uc[0].x * wc[2].x, uc[2].y * wc[0].y - uc[0].y * wc[2].y};
     b0[2] = F2{uc[0].x * wc[1].x - uc[1].x * wc[0].x, uc[0].y * wc[1].y - uc[1].y * wc[0].y};
 
     // ---- omega2 of plane zc = zf - 1 (needs buf(zf), buf(zf - 2) own; buf(zf - 1) neighbours)
     const int zc = zf - 1;
-    F2 q1[3];
     {
       const F2 bxu = sb_ld2(sr + 0 * FV::ARR + soff + FV::ROW), bxd = sb_ld2(sr + 0 * FV::ARR + soff - FV::ROW);
       const F2 bzu = sb_ld2(sr + 1 * FV::ARR + soff + FV::ROW), bzd = sb_ld2(sr + 1 * FV::ARR + soff - FV::ROW);
@@ -332,13 +327,13 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
       q1[1] = wp[1];
       q1[2] = wp[2];
       if (wr0) {
-        q1[0].x += p * (bzu.x - bzd.x - b0[1].x + b2xy[1].x);
-        q1[1].x += p * (b0[0].x - b2xy[0].x - b1[2].y + bzl);
+        q1[0].x += p * (bzu.x - bzd.x - b0[1].x + b2[1].x);
+        q1[1].x += p * (b0[0].x - b2[0].x - b1[2].y + bzl);
         q1[2].x += p * (b1[1].y - byl - bxu.x + bxd.x);
       }
       if (wr1) {
-        q1[0].y += p * (bzu.y - bzd.y - b0[1].y + b2xy[1].y);
-        q1[1].y += p * (b0[0].y - b2xy[0].y - bzr + b1[2].x);
+        q1[0].y += p * (bzu.y - bzd.y - b0[1].y + b2[1].y);
+        q1[1].y += p * (b0[0].y - b2[0].y - bzr + b1[2].x);
         q1[2].y += p * (byr - b1[1].x - bxu.y + bxd.y);
       }
     }
@@ -357,12 +352,12 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
         const float ql = __shfl_up_sync(0xffffffffu, q2[c].y, 1), qr = __shfl_down_sync(0xffffffffu, q2[c].x, 1);
         r[c] = q2[c];
         if (lap0) {
-          const float s = q2[c].y + ql + qu.x + qd.x + q1[c].x + q3[c].x;
-          r[c].x += d * (s - 6.f * q2[c].x);
+          const float sum = q2[c].y + ql + qu.x + qd.x + q1[c].x + q3[c].x;
+          r[c].x += d * (sum - 6.f * q2[c].x);
         }
         if (lap1) {
-          const float s = qr + q2[c].x + qu.y + qd.y + q1[c].y + q3[c].y;
-          r[c].y += d * (s - 6.f * q2[c].y);
+          const float sum = qr + q2[c].x + qu.y + qd.y + q1[c].y + q3[c].y;
+          r[c].y += d * (sum - 6.f * q2[c].y);
         }
       }
       if (st_row) {
@@ -378,8 +373,6 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
           }
         }
       }
-    } else {
-      // (the shuffles above are warp-collective: keep every lane on the same path) -- nothing to do
     }
     // ---- publish this iteration's planes for the y neighbours of the next one
     sb_st2(sw + 0 * FV::ARR + soff, b0[0]);
@@ -388,19 +381,25 @@ SB_D void sb_vorticity_fused_v2_body(const SbGeom& g, float* __restrict__ out, c
     sb_st2(sw + 3 * FV::ARR + soff, q1[1]);
     sb_st2(sw + 4 * FV::ARR + soff, q1[2]);
     __syncthreads();
-    // ---- shift the z history
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      q3[c] = q2[c];
-      q2[c] = q1[c];
-      wp[c] = wc[c];
-    }
-    b2xy[0] = b1[0];
-    b2xy[1] = b1[1];
-    b1[0] = b0[0];
-    b1[1] = b0[1];
-    b1[2] = b0[2];
+  };
+
+  F2 W[3][3] = {}, U[2][3] = {}, B[3][3] = {}, Q[3][3] = {};
+  load_plane(zb - 2, W[0], U[0]);
+  const int zlast = ze + 1;
+  // step k of a period: current plane in W[k % 3] / U[k % 2], results into B[k % 3] / Q[k % 3]
+#define SB_FUSED_STEP(k)                                                                                     \
+  step(zf, W[((k) + 1) % 3], U[((k) + 1) % 2], W[(k) % 3], U[(k) % 2], W[((k) + 2) % 3], B[(k) % 3],         \
+       B[((k) + 2) % 3], B[((k) + 1) % 3], Q[(k) % 3], Q[((k) + 2) % 3], Q[((k) + 1) % 3]);                  \
+  if (++zf > zlast) break;
+  for (int zf = zb - 2;;) {
+    SB_FUSED_STEP(0)
+    SB_FUSED_STEP(1)
+    SB_FUSED_STEP(2)
+    SB_FUSED_STEP(3)
+    SB_FUSED_STEP(4)
+    SB_FUSED_STEP(5)
   }
+#undef SB_FUSED_STEP
 }
 
 template <int R>

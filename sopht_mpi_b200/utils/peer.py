@@ -40,7 +40,12 @@ class PeerExchange:
         self.rank, self.nranks, self.device = rank, nranks, device
         self.n_buffers, self.n_float32 = n_buffers, int(n_float32)
         self.transport = os.environ.get("SB200_EXCHANGE", "push")
-        self.blocks_per_peer = int(os.environ.get("SB200_PUSH_BLOCKS", "0"))
+        # thread blocks per destination: ~32 blocks of 512 threads saturate one NVLink port pair
+        # (tools/ubench/peer_copy.py: 8 -> 364, 16 -> 630, 32 -> 658 GB/s); with P - 1 destinations in
+        # flight the egress limit is shared, so fewer blocks per destination leave more SMs to the
+        # transform kernels the exchange overlaps
+        default_blocks = max(4, -(-40 // max(nranks - 1, 1)))
+        self.blocks_per_peer = int(os.environ.get("SB200_PUSH_BLOCKS", "0")) or default_blocks
         if self.transport == "nccl":
             use_peer_copies = False
         self._lib = _lib.load() if device.type == "cuda" else None
