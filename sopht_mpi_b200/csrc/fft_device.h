@@ -26,6 +26,9 @@ template <typename T>
 SB_HD C2<T> cscale(C2<T> a, T s) { return C2<T>{a.x * s, a.y * s}; }
 template <typename T>
 SB_HD C2<T> cconj(C2<T> a) { return C2<T>{a.x, -a.y}; }
+// conj(a) * s
+template <typename T>
+SB_HD C2<T> cscale_conj(C2<T> a, T s) { return C2<T>{a.x * s, a.y * -s}; }
 // multiply by -i  (forward quarter turn)
 template <typename T>
 SB_HD C2<T> cmul_mi(C2<T> a) { return C2<T>{a.y, -a.x}; }
@@ -87,6 +90,13 @@ SB_HD C2<float> cscale(C2<float> a, float s) {
   return sb_up(sb_mul2(sb_pk(a.x, a.y), sb_pk(s, s)));
 #else
   return C2<float>{a.x * s, a.y * s};
+#endif
+}
+SB_HD C2<float> cscale_conj(C2<float> a, float s) {
+#ifdef __CUDA_ARCH__
+  return sb_up(sb_mul2(sb_pk(a.x, a.y), sb_pk(s, -s)));
+#else
+  return C2<float>{a.x * s, a.y * -s};
 #endif
 }
 SB_HD C2<float> cmul(C2<float> a, C2<float> b) {
@@ -669,4 +679,148 @@ SB_D void sb_fft32_inverse_c(C2<T> (&v)[SB_FFT_P32], int t, const C2<T>* __restr
   sb_fft32_forward_c<T, LOG2N, LINES, TRAIL>(v, t, tw, sl);
 #pragma unroll
   for (int p = 0; p < SB_FFT_P32; ++p) v[p].y = -v[p].y;
+}
+
+// ------------------------------------------------------------------ one line per warp (float)
+// The same 32-point-per-thread transform with the line's n / 32 threads INSIDE one warp (lanes t of a
+// warp for n = 1024, half a warp for n = 512): the exchange between the two register stages is warp
+// local, so the only synchronisation is __syncwarp and the warps of a block never wait for each other.
+// The exchange buffer holds ONE float per element (real parts first, then the imaginary parts through the
+// same words): half the shared memory of the complex exchange, 32-bit accesses at thread stride 33 /
+// unit stride are conflict-free.
+
+// DFT-16 of a[0..7] with a[8..15] = 0 (zero-padded line): the first radix-4 layer needs half its adds
+template <typename T>
+SB_D void dft16_upper_zero(C2<T>* a) {
+  const T c1 = T(0.92387953251128675613), s1 = T(0.38268343236508977173);
+  const T h = T(0.70710678118654752440);
+  C2<T> b[4][4];  // b[n2][k1]
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) {
+    const C2<T> a0 = a[n2], a1 = a[n2 + 4], m = cmul_mi(a1);
+    b[n2][0] = cadd(a0, a1);
+    b[n2][1] = cadd(a0, m);
+    b[n2][2] = csub(a0, a1);
+    b[n2][3] = csub(a0, m);
+  }
+  const C2<T> w1{c1, -s1}, w2{h, -h}, w3{s1, -c1}, w6{-h, -h}, w9{-c1, s1};
+  b[1][1] = cmul(b[1][1], w1);
+  b[1][2] = cmul(b[1][2], w2);
+  b[1][3] = cmul(b[1][3], w3);
+  b[2][1] = cmul(b[2][1], w2);
+  b[2][2] = cmul_mi(b[2][2]);
+  b[2][3] = cmul(b[2][3], w6);
+  b[3][1] = cmul(b[3][1], w3);
+  b[3][2] = cmul(b[3][2], w6);
+  b[3][3] = cmul(b[3][3], w9);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    dft4(b[0][k1], b[1][k1], b[2][k1], b[3][k1]);
+    a[k1] = b[0][k1];
+    a[k1 + 4] = b[1][k1];
+    a[k1 + 8] = b[2][k1];
+    a[k1 + 12] = b[3][k1];
+  }
+}
+
+// DFT-32 of a[0..15] with a[16..31] = 0 on entry (UPPER_ZERO), all 32 outputs
+template <typename T, bool UPPER_ZERO>
+SB_D void dft32_p(C2<T>* a) {
+  if constexpr (!UPPER_ZERO) {
+    dft32<T>(a);
+  } else {
+    C2<T> e[16], o[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      e[k] = a[2 * k];
+      o[k] = a[2 * k + 1];
+    }
+    dft16_upper_zero<T>(e);
+    dft16_upper_zero<T>(o);
+    constexpr double c[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                              0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                              0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
+                              -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                              -0.92387953251128675613, -0.98078528040323044913};
+    constexpr double sn[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                               0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
+                               0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
+                               0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                               0.38268343236508977173, 0.19509032201612826785};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      C2<T> w;
+      if (k == 0)
+        w = o[0];
+      else if (k == 8)
+        w = cmul_mi(o[8]);
+      else
+        w = cmul(o[k], C2<T>{T(c[k]), T(-sn[k])});
+      a[k] = cadd(e[k], w);
+      a[k + 16] = csub(e[k], w);
+    }
+  }
+}
+
+// scheduling fence on the 64 data registers: everything before it is complete and nothing after it has
+// started, which keeps ptxas from interleaving two register stages (and spilling)
+SB_D void sb_reg_fence(C2<float> (&v)[SB_FFT_P32]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int p = 0; p < SB_FFT_P32; ++p) asm volatile("" : "+f"(v[p].x), "+f"(v[p].y));
+#else
+  (void)v;
+#endif
+}
+
+template <int LOG2N>
+struct SbFft32W {
+  using P = SbFft32C<LOG2N>;
+  // floats per exchange line: n + n/32 pads, rounded so that lines start on 16 bytes (they also stage the
+  // line's Green's factors, a bulk copy) and, for n = 512 (two lines per warp), sit 16 banks apart
+  static constexpr int XL = P::Tn == 32 ? P::n + P::n / 32 + 4 : P::n + P::n / 32;
+  static_assert(XL % 4 == 0 && (P::Tn == 32 || (XL % 32) == 16), "exchange line stride");
+};
+
+// forward transform, v[p] <-> element t + p Tn on entry and on return; xl = this line's exchange floats
+// (element e at padded position e + (e >> 5): scatter at thread stride 33, re-read at unit stride).
+// UPPER_ZERO: v[16..31] are zero on entry (and need not be initialised).
+template <int LOG2N, bool UPPER_ZERO>
+SB_D void sb_fft32w_forward(C2<float> (&v)[SB_FFT_P32], int t, const C2<float>* __restrict__ tw, float* xl) {
+  using P = SbFft32C<LOG2N>;
+  dft32_p<float, UPPER_ZERO>(v);
+  (void)tw;
+  float* dst = xl + 33 * t;
+  __syncwarp();  // the previous readers of this buffer are done
+#pragma unroll
+  for (int q = 0; q < SB_FFT_P32; ++q) dst[q] = v[q].x;
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < SB_FFT_P32; ++p) v[p].x = xl[t + p * P::Tn + ((p * P::Tn) >> 5)];
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < SB_FFT_P32; ++q) dst[q] = v[q].y;
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < SB_FFT_P32; ++p) v[p].y = xl[t + p * P::Tn + ((p * P::Tn) >> 5)];
+}
+// ... second register stage (after the exchange); split from the first so that the caller can reuse the
+// exchange buffer in between
+template <int LOG2N>
+SB_D void sb_fft32w_second(C2<float> (&v)[SB_FFT_P32], int t, const C2<float>* __restrict__ tw) {
+  using P = SbFft32C<LOG2N>;
+#pragma unroll
+  for (int m = 0; m < P::M; ++m) {
+    C2<float> pw[P::NB];
+    const int k = t + m * P::Tn;
+#pragma unroll
+    for (int b = 0; b < P::NB; ++b) pw[b] = tw[k << b];
+    C2<float> a[P::R2];
+#pragma unroll
+    for (int q = 0; q < P::R2; ++q) a[q] = v[m + P::M * q];
+    sb_twiddle_apply_base32<float, P::R2>(a, pw);
+    dft_small32<float, P::R2>(a);
+#pragma unroll
+    for (int q = 0; q < P::R2; ++q) v[m + P::M * q] = a[q];
+  }
 }

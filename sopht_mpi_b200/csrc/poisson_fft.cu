@@ -52,8 +52,11 @@ struct SbLines {
   // group i >> gsh, groups are s_grp elements apart.  gsh = 31: plain (line i at element i).
   int gsh = 31;
   long long s_grp = 0;
+  // rot = 7: the 8 lines of a group are rotated by (o1 >> 1) & 7 slots inside their 64-byte row (o1 = z in
+  // the y passes), which makes the column reads of the one-line-per-warp z kernel bank-conflict free
+  int rot = 0;
   SB_HD long long base(int i, int o1, int o2) const {
-    return (i & ((1u << gsh) - 1)) + (long long)(i >> gsh) * s_grp +
+    return ((i + ((o1 >> 1) & rot)) & ((1u << gsh) - 1)) + (long long)(i >> gsh) * s_grp +
            (long long)(o1 & ((1 << o1_shift) - 1)) * s1 + (long long)(o1 >> o1_shift) * s1_hi + o2 * s2;
   }
   SB_HD long long point(int t, int p, int Tn) const {
@@ -548,12 +551,91 @@ SB_D void sb_mbar_wait(unsigned long long* bar, unsigned parity) {
         : "memory");
   } while (!ok);
 }
-#else
-SB_D void sb_mbar_init(unsigned long long*, unsigned) {}
-SB_D void sb_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) {
-  memcpy(smem_dst, gsrc, bytes);
+// the same for a CONVERGED warp: the retry branch is taken on a warp vote, i.e. uniformly, so ptxas keeps
+// treating the warp as converged (a per-thread retry loop in front of a __syncwarp makes it emit the
+// out-of-line reconvergence path, with ~300 bytes of spills around it in the fused z kernel)
+SB_D void sb_mbar_wait_warp(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(sb_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!__all_sync(0xffffffffu, ok));
 }
-SB_D void sb_mbar_wait(unsigned long long*, unsigned) {}
+// arm + copy for one thread of a converged warp, PREDICATED instead of branched (a divergent branch in
+// front of a __syncwarp makes ptxas emit its out-of-line reconvergence path); several copies may follow
+// one arming with the total byte count
+SB_D void sb_mbar_expect_if(bool pred, unsigned long long* bar, unsigned bytes) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n"
+      "@p fence.proxy.async.shared::cta;\n"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%2], %1;\n}" ::"r"((unsigned)pred),
+      "r"(bytes), "r"(sb_smem_u32(bar))
+      : "memory");
+}
+SB_D void sb_bulk_copy_if(bool pred, void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%4];\n}" ::"r"(
+          (unsigned)pred),
+      "r"(sb_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(sb_smem_u32(bar))
+      : "memory");
+}
+SB_D void sb_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sb_smem_u32(bar)) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the bulk-copy engine
+SB_D void sb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared -> global bulk copy (one thread), completion tracked by the thread's bulk group
+SB_D void sb_bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sb_smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+SB_D void sb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+SB_D void sb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+SB_D void sb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+// emulation: the barrier word is [completed phases : 32][bytes / 16 in flight : 16][arrival count : 8][pending : 8]
+SB_D void sb_mbar_init(unsigned long long* bar, unsigned count) {
+  __atomic_store_n(bar, ((unsigned long long)count << 8) | count, __ATOMIC_SEQ_CST);
+}
+// pending -= arrivals, in-flight += tx16 (may be negative); the phase completes when both reach zero
+SB_D void sb_mbar_update(unsigned long long* bar, unsigned arrivals, long long tx16) {
+  unsigned long long e = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+  for (;;) {
+    const unsigned long long cnt = (e >> 8) & 0xffu, pend = (e & 0xffu) - arrivals;
+    const unsigned long long tx = (unsigned long long)((long long)((e >> 16) & 0xffffu) + tx16) & 0xffffu;
+    unsigned long long d = (e & 0xffffffff00000000ULL) | (tx << 16) | (cnt << 8) | pend;
+    if (pend == 0 && tx == 0) d = (((e >> 32) + 1) << 32) | (cnt << 8) | cnt;
+    if (__atomic_compare_exchange_n(bar, &e, d, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return;
+  }
+}
+SB_D void sb_mbar_arrive(unsigned long long* bar) { sb_mbar_update(bar, 1, 0); }
+SB_D void sb_mbar_expect_if(bool pred, unsigned long long* bar, unsigned bytes) {
+  if (pred) sb_mbar_update(bar, 1, bytes / 16);
+}
+SB_D void sb_bulk_copy_if(bool pred, void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  if (!pred) return;
+  memcpy(smem_dst, gsrc, bytes);
+  sb_mbar_update(bar, 0, -(long long)(bytes / 16));
+}
+SB_D void sb_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  sb_mbar_expect_if(true, bar, bytes);
+  sb_bulk_copy_if(true, smem_dst, gsrc, bytes, bar);
+}
+SB_D void sb_mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (((__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 32) & 1u) == parity) std::this_thread::yield();
+}
+SB_D void sb_mbar_wait_warp(unsigned long long* bar, unsigned parity) { sb_mbar_wait(bar, parity); }
+SB_D void sb_fence_async_smem() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+SB_D void sb_bulk_store(void* gdst, const void* smem_src, unsigned bytes) { memcpy(gdst, smem_src, bytes); }
+SB_D void sb_bulk_wait_read() {}
+SB_D void sb_bulk_wait_all() {}
+SB_D void sb_prefetch_l2(const void*) {}
 #endif
 
 constexpr int sb_zconv_blocks(int log2n) { return log2n >= 10 ? 2 : 4; }
@@ -616,6 +698,112 @@ __global__ void __launch_bounds__(8 * ((1 << LOG2N) / SB_FFT_P32), sb_zconv_bloc
   }
 }
 
+// ------------------------------------------------------ fused z pass, one line per warp
+// Same transform and tile layout as sb_fft_zconv32_kernel, organised so that no warp ever waits for
+// another one inside the transform (that kernel: 4 block barriers per tile, 2 resident blocks, FMA pipe
+// 56 % busy).  A line's n / 32 threads sit inside ONE warp (fft_device.h, sb_fft32w_forward), so:
+//   * the register-stage exchange is warp local (__syncwarp only);
+//   * a warp reads its line from the landed tile and writes the result back to the SAME slots: the tile
+//     buffer needs no block barrier either.  Reading column l of the [z][8] tile would be an 8- to 16-way
+//     bank conflict, therefore the y passes store the tile with its 64-byte rows rotated by (z >> 1) & 7
+//     slots (SbLines::rot): a warp's 32 (16) consecutive z then fall on distinct banks;
+//   * tiles move in AND out with bulk copies (cp.async.bulk, mbarrier / bulk-group completion); two tile
+//     buffers per block alternate; the warp that writes the LAST line of a tile (shared-memory arrival
+//     counter) stores the tile and re-arms the buffer with the tile after next, nobody waits for it;
+//   * the Green's factors (g5[m1][kx group][line][n] floats, natural bin order) are staged per warp by a
+//     bulk copy into the warp's own exchange line, which is idle between the two transforms; the copy
+//     overlaps the second register stage of the forward transform.
+template <int LOG2N>
+struct SbZw {
+  using FC = SbFft32C<LOG2N>;
+  static constexpr int Tn = FC::Tn, LINES = 8, NT = LINES * Tn, NW = NT / 32, NZ = FC::n / 2;
+  static constexpr unsigned TILE = NZ * LINES;  // complex elements of a tile
+  static constexpr int XL = SbFft32W<LOG2N>::XL;
+  static constexpr int BLOCKS = LOG2N >= 10 ? 2 : 4;
+  static constexpr size_t smem = 2 * TILE * sizeof(C2<float>) + (size_t)LINES * XL * sizeof(float) + 128;
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(SbZw<LOG2N>::NT, SbZw<LOG2N>::BLOCKS)
+    sb_fft_zconvw_kernel(C2<float>* B, int ntiles, int ncomp, int ng, int nky, const C2<float>* __restrict__ tw,
+                         const float* __restrict__ g5, int n1_full) {
+  using Z = SbZw<LOG2N>;
+  constexpr int PT = SB_FFT_P32, Tn = Z::Tn, N = Z::FC::n;
+  constexpr unsigned TILE = Z::TILE, TILE_BYTES = TILE * sizeof(C2<float>);
+  SB_DYN_SMEM(smem_raw);
+  C2<float>* tbuf = reinterpret_cast<C2<float>*>(smem_raw);  // two tiles [nz][8]
+  float* xch = reinterpret_cast<float*>(tbuf + 2 * TILE);    // exchange lines
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(xch + Z::LINES * Z::XL);  // full[2], green[NW]
+  unsigned* cnt = reinterpret_cast<unsigned*>(bars + 2 + Z::NW);  // lines written per tile buffer
+  const int tid = threadIdx.x, l = tid / Tn, t = tid % Tn, lane = tid & 31, warp = tid >> 5;
+  float* xl = xch + l * Z::XL;
+  const int slot = (l + (t >> 1)) & 7;  // (z >> 1) & 7 == (t >> 1) & 7 for every z = t + p Tn of this thread
+  auto tile_offset = [&](int tile) {
+    const int c = tile % ncomp, r = tile / ncomp;
+    return (((long long)c * ng + r % ng) * nky + r / ng) * (long long)TILE;
+  };
+  if (tid == 0) {
+    sb_mbar_init(bars + 0, 1);
+    sb_mbar_init(bars + 1, 1);
+    for (int w = 0; w < Z::NW; ++w) sb_mbar_init(bars + 2 + w, 1);
+    cnt[0] = cnt[1] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int tile = blockIdx.x;
+    if (tile < ntiles) sb_bulk_load(tbuf, B + tile_offset(tile), TILE_BYTES, bars + 0);
+    tile += gridDim.x;
+    if (tile < ntiles) sb_bulk_load(tbuf + TILE, B + tile_offset(tile), TILE_BYTES, bars + 1);
+  }
+  int k = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    const int b = k & 1;
+    C2<float>* tb = tbuf + b * TILE + slot;
+    sb_mbar_wait_warp(bars + b, (unsigned)(k >> 1) & 1u);
+    C2<float> v[PT];
+#pragma unroll
+    for (int p = 0; p < PT / 2; ++p) v[p] = tb[(t + p * Tn) * Z::LINES];
+    sb_fft32w_forward<LOG2N, true>(v, t, tw, xl);
+    // the exchange buffer is idle until the next transform: stage this warp's Green's factors in it
+    // (n floats per line, natural bin order) while the second register stage runs
+    __syncwarp();
+    {
+      const int r = tile / ncomp, kxg = r % ng, ky = r / ng;
+      const int m1 = ky <= (n1_full >> 1) ? ky : n1_full - ky;
+      constexpr int LW = 32 / Tn;  // lines per warp
+      const float* src = g5 + (((long long)m1 * ng + kxg) * Z::LINES + warp * LW) * N;
+      sb_mbar_expect_if(lane == 0, bars + 2 + warp, LW * N * sizeof(float));
+#pragma unroll
+      for (int i = 0; i < LW; ++i)
+        sb_bulk_copy_if(lane == 0, xch + (warp * LW + i) * Z::XL, src + i * N, N * sizeof(float), bars + 2 + warp);
+    }
+    sb_fft32w_second<LOG2N>(v, t, tw);
+    sb_mbar_wait_warp(bars + 2 + warp, (unsigned)k & 1u);
+    // x Green's factor, and the conjugation that turns the second forward transform into the inverse
+#pragma unroll
+    for (int p = 0; p < PT; ++p) v[p] = cscale_conj(v[p], xl[t + p * Tn]);
+    sb_fft32w_forward<LOG2N, false>(v, t, tw, xl);
+    sb_fft32w_second<LOG2N>(v, t, tw);
+#pragma unroll
+    for (int p = 0; p < PT / 2; ++p) tb[(t + p * Tn) * Z::LINES] = C2<float>{v[p].x, -v[p].y};
+    sb_fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if ((atomicAdd(cnt + b, 1u) + 1) % Z::NW == 0) {  // last line of the tile: store it, re-arm the buffer
+        __threadfence_block();
+        sb_bulk_store(B + tile_offset(tile), tbuf + b * TILE, TILE_BYTES);
+        const long long next = (long long)tile + 2LL * gridDim.x;
+        if (next < ntiles) {
+          sb_bulk_wait_read();
+          sb_bulk_load(tbuf + b * TILE, B + tile_offset((int)next), TILE_BYTES, bars + b);
+        }
+      }
+    }
+  }
+  if (lane == 0) sb_bulk_wait_all();
+}
+
 // Re(spectrum) * scale -> mirror-compressed table
 template <typename T>
 struct GreensExtractOp {
@@ -640,13 +828,27 @@ struct GreensThreadOrderOp {
   int n, Tn, lines, nib, pitch;
   int kx0, inner;  // first global kx of this rank's lines, number of lines
   int pt;          // bins per thread (16 or 32)
+  int warp_order = 0;  // 1: g5[m1][ib][l][n] (natural bin order per line, sb_fft_zconvw_kernel)
   SB_D void operator()(long long idx) const {
-    const int p = (int)(idx % pt);
-    long long r = idx / pt;
-    const int l = (int)(r % lines);
-    r /= lines;
-    const int t = (int)(r % Tn);
-    r /= Tn;
+    int p, l, t;
+    long long r;
+    if (warp_order) {
+      const int k = (int)(idx % n), mk = k <= (n >> 1) ? k : n - k;
+      r = idx / n;
+      l = (int)(r % lines);
+      r /= lines;
+      const int ib = (int)(r % nib), i = ib * lines + l, kx = kx0 + i;
+      const long long m1 = r / nib;
+      g2[idx] = (i < inner && kx < pitch) ? g[mk * g_pt + m1 * g_s1 + kx] : T(0);
+      return;
+    } else {
+      p = (int)(idx % pt);
+      r = idx / pt;
+      l = (int)(r % lines);
+      r /= lines;
+      t = (int)(r % Tn);
+      r /= Tn;
+    }
     const int ib = (int)(r % nib);
     const long long m1 = r / nib;
     const int k = t + p * Tn, mk = k <= (n >> 1) ? k : n - k, i = ib * lines + l, kx = kx0 + i;
@@ -905,10 +1107,48 @@ static int launch_zconv32(C2<float>* B, int ncomp, int ng, int nky, const C2<flo
   SB_CHECK_LAUNCH("fft_zconv32");
   return 0;
 }
+template <int LOG2N>
+static int launch_zconvw(C2<float>* B, int ncomp, int ng, int nky, const C2<float>* tw, const float* g3,
+                         int n1_full, void* stream) {
+  using Z = SbZw<LOG2N>;
+  SB_KERNEL_ATTR_SMEM((sb_fft_zconvw_kernel<LOG2N>), Z::smem);
+  const long long ntiles = (long long)ncomp * ng * nky;
+  long long resident = 148LL * Z::BLOCKS;
+#ifndef SB200_EMU
+  {
+    static long long cached = 0;
+    if (cached == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_fft_zconvw_kernel<LOG2N>, Z::NT, Z::smem);
+      cached = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    }
+    resident = cached;
+  }
+#else
+  resident = 3;  // a few persistent "blocks", several tiles each
+#endif
+  const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+  SB_LAUNCH_COOP((sb_fft_zconvw_kernel<LOG2N>), dim3(grid), dim3(Z::NT), Z::smem, stream, B, (int)ntiles, ncomp, ng,
+                 nky, tw, g3, n1_full);
+  SB_CHECK_LAUNCH("fft_zconvw");
+  return 0;
+}
+// fused z kernel on the tile-contiguous layout: 0 off, 1 block-synchronous (sb_fft_zconv32_kernel),
+// 2 one line per warp (sb_fft_zconvw_kernel, default); SB200_ZCONV is a developer knob
+static inline int sb_zconv_mode() {
+  static const int mode = getenv("SB200_ZCONV") ? atoi(getenv("SB200_ZCONV")) : 2;
+  return mode;
+}
 template <typename T>
 static int launch_zconv(int log2n, C2<T>* B, int ncomp, int ng, int nky, const C2<T>* tw, const T* g2, int n1_full,
                         void* stream) {
   if constexpr (sizeof(T) == 4) {
+    if (sb_zconv_mode() == 2) {
+      if (log2n == 9) return launch_zconvw<9>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
+      if (log2n == 10) return launch_zconvw<10>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
+    }
     if (log2n == 9) return launch_zconv32<9>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
     if (log2n == 10) return launch_zconv32<10>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
   }
@@ -951,8 +1191,7 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
   {
     const int inner = p->nranks > 1 ? st->kxl : nx + 1;
     st->ng = (inner + 7) / 8;
-    static const bool env_off = getenv("SB200_ZCONV") && atoi(getenv("SB200_ZCONV")) == 0;
-    st->zconv = !env_off && sizeof(T) == 4 && p->dim == 3 && (st->pz.log2n == 9 || st->pz.log2n == 10) &&
+    st->zconv = sb_zconv_mode() != 0 && sizeof(T) == 4 && p->dim == 3 && (st->pz.log2n == 9 || st->pz.log2n == 10) &&
                 sb_use_p32(1, st->pz.log2n);
   }
   const size_t b_bytes = p->dim != 3 ? 0
@@ -1002,11 +1241,12 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
     const int Tn = 2 * nz / pt;
     const int inner = p->nranks > 1 ? st->kxl : nx + 1, kx0 = p->nranks > 1 ? p->rank * st->kxl : 0;
     const int nib = (inner + lines - 1) / lines;
-    const long long count = (long long)(ny + 1) * nib * Tn * lines * pt;
+    const bool line_order = st->zconv && sb_zconv_mode() == 2;
+    const long long count = (long long)(ny + 1) * nib * Tn * lines * pt;  // (both orders: n floats per line)
     SB_REQUIRE(SB_DEV_ALLOC(st->G2, sizeof(T) * count), "fft backend: cannot allocate the thread-order table");
     st->bytes += sizeof(T) * count;
     e = sb_launch_flat(count, GreensThreadOrderOp<T>{st->G2, st->G, (long long)(ny + 1) * P, P, 2 * nz, Tn, lines,
-                                                     nib, (int)P, kx0, inner, pt},
+                                                     nib, (int)P, kx0, inner, pt, line_order},
                        stream, "greens_thread_order");
   }
   SB_STREAM_SYNC(stream);
@@ -1038,6 +1278,7 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
       SbLines lb{nx + 1, nz, ncomp, 8, (long long)st->ng * NKY * tile, tile};
       lb.gsh = 3;
       lb.s_grp = NKY * tile;
+      lb.rot = sb_zconv_mode() == 2 ? 7 : 0;
       if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
       st->mark(2, stream);
       if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * ny, stream))) return e;
@@ -1207,6 +1448,7 @@ static int slab_spectral_t(sb200_poisson* p, void* recv, int ncomp, void* stream
     SbLines lb{sp.kxl, p->nz, ncomp, 8, (long long)st->ng * NKY * tile, tile};
     lb.gsh = 3;
     lb.s_grp = NKY * tile;
+    lb.rot = sb_zconv_mode() == 2 ? 7 : 0;
     if ((e = launch_strided<T, 0>(st->py, (const C2<T>*)recv, sp.lr, st->B, lb, st->twy, none, stream))) return e;
     if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * p->ny, stream)))
       return e;

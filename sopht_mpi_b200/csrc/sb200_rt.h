@@ -77,6 +77,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
 #define SB_KERNEL_ATTR_SMEM(kernel, bytes) (0)
 
 static inline void __syncthreads() { sbemu::t_ctx->block_bar->arrive_and_wait(); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
   sbemu::t_ctx->warp_bar[sbemu::t_linear_tid / 32]->arrive_and_wait();
 }
