@@ -650,4 +650,5 @@ def test_flow_past_sphere_example_with_the_in_repo_forcing_grid(cuda):
     interactor.compute_flow_forces_and_torques()
     vbf_o.compute_interaction_force_on_lag_grid(ora.velocity_field, grid.position_field, grid.velocity_field)
     assert _rel(interactor.global_lag_grid_forcing_field, vbf_o.forcing) <= 1e-4
-    assert np.allclose(interactor.body_flow_forces[:, 0], -vbf_o.forcing.sum(axis=1), rtol=1e-3, atol=1e-9)
+    want = -vbf_o.forcing.sum(axis=1)  # the transverse components cancel to rounding noise
+    assert np.allclose(interactor.body_flow_forces[:, 0], want, rtol=1e-3, atol=1e-5 * np.abs(want).max())
