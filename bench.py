@@ -373,6 +373,8 @@ def main():
 
     name = args.workload or DEFAULT_WORKLOAD
     grid = list(WORKLOADS[name][0])
+    if os.environ.get("SB200_BENCH_GRID"):  # developer aid (e.g. the per-rank slab of a larger job on fewer GPUs)
+        grid = [int(v) for v in os.environ["SB200_BENCH_GRID"].split(",")]
     if args.scaling == "weak" and world > 1:
         # fixed cells per GPU: the box doubles along z, then y, then x; the decomposition stays z-slabs
         f, axis = world, 0
@@ -459,6 +461,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
     clocks = sampler.stop() if sampler else {}
+
+    if os.environ.get("SB200_TRACE"):
+        # developer aid: kernel-level timeline (CUPTI through torch.profiler) of three more steps, one
+        # chrome trace per rank; read with tools/trace_summary.py
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                one_step()
+            barrier()
+        prof.export_chrome_trace(f"{os.environ['SB200_TRACE']}_rank{rank}.json")
 
     # ---- per-stage device times (untimed extra pass) -> roofline of the dominant stage
     stage_ms = {}

@@ -250,6 +250,7 @@ class MPIGhostCommunicator:
         self.full_exchange = full_exchange
         self.grid_coord = np.array(mpi_construct.grid.coords)
         self.comm_requests = []
+        self._peer_pending = []  # (halo, ticket, fields) of exchanges that went through peer memory
         self._recv_staging = []
         # fields whose ghost planes are known to be current: (data_ptr, host-write version) of the last
         # exchange; the owner of a field drops the entry when a kernel rewrites it (``mark_stale``)
@@ -288,6 +289,23 @@ class MPIGhostCommunicator:
         mc = self.mpi_construct
         gs = self.ghost_size
         ops = []
+        if mc.size > 1 and fields and all(t.is_cuda for t in fields):
+            # boundary planes straight into the neighbours' mailboxes (utils/peer.py:PeerHalo)
+            from .peer import peer_halo
+
+            if mc.periodic_domain:
+                for t in fields:
+                    self._wrap_local_axes(t)
+            up, down = [t[-2 * gs:-gs] for t in fields], [t[gs:2 * gs] for t in fields]
+            halo = peer_halo(mc, up[0].numel() * up[0].element_size())
+            if halo is not None and halo.usable(up, down):
+                self._peer_pending.append((halo, halo.send(up, down), list(fields)))
+                return
+            for t in fields:
+                ops += self._plane_ops(t)
+            if ops:
+                self.comm_requests += dist.batch_isend_irecv(ops)
+            return
         for t in fields:
             if mc.periodic_domain:
                 self._wrap_local_axes(t)
@@ -318,6 +336,20 @@ class MPIGhostCommunicator:
         for req in self.comm_requests:
             req.wait()
         self.comm_requests = []
+        gs = self.ghost_size
+        for halo, ticket, fields in self._peer_pending:
+            n, nbytes = len(fields), ticket[4] or fields[0][:gs].numel() * fields[0].element_size()
+            from_prev, from_next = halo.wait(ticket, n, n)
+            dst, src = [], []
+            for c, t in enumerate(fields):
+                if halo.prev is not None:
+                    dst.append(t[:gs].data_ptr())
+                    src.append(from_prev + c * nbytes)
+                if halo.next is not None:
+                    dst.append(t[-gs:].data_ptr())
+                    src.append(from_next + c * nbytes)
+            halo.copy_blocks(dst, src, nbytes)
+        self._peer_pending = []
 
     # ---- ghost freshness (B200 build): lets the simulator skip an exchange of a field whose ghost
     # planes were filled since it was last written (the interactor exchanges the velocity right before
