@@ -721,12 +721,13 @@ struct SbZw {
   static constexpr int XL = SbFft32W<LOG2N>::XL;
   static constexpr int BLOCKS = LOG2N >= 10 ? 2 : 4;
   static constexpr size_t smem = 2 * TILE * sizeof(C2<float>) + (size_t)LINES * XL * sizeof(float) + 128;
+  static_assert((2 + NW) * 8 + 2 * 4 + 2 * 4 <= 128, "barriers, arrival counters, tile ids");
 };
 
 template <int LOG2N>
 __global__ void __launch_bounds__(SbZw<LOG2N>::NT, SbZw<LOG2N>::BLOCKS)
     sb_fft_zconvw_kernel(C2<float>* B, int ntiles, int ncomp, int ng, int nky, const C2<float>* __restrict__ tw,
-                         const float* __restrict__ g5, int n1_full) {
+                         const float* __restrict__ g5, int n1_full, int* next_tile) {
   using Z = SbZw<LOG2N>;
   constexpr int PT = SB_FFT_P32, Tn = Z::Tn, N = Z::FC::n;
   constexpr unsigned TILE = Z::TILE, TILE_BYTES = TILE * sizeof(C2<float>);
@@ -735,12 +736,25 @@ __global__ void __launch_bounds__(SbZw<LOG2N>::NT, SbZw<LOG2N>::BLOCKS)
   float* xch = reinterpret_cast<float*>(tbuf + 2 * TILE);    // exchange lines
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(xch + Z::LINES * Z::XL);  // full[2], green[NW]
   unsigned* cnt = reinterpret_cast<unsigned*>(bars + 2 + Z::NW);  // lines written per tile buffer
+  int* tile_of = reinterpret_cast<int*>(cnt + 2);                  // tile held by each buffer
   const int tid = threadIdx.x, l = tid / Tn, t = tid % Tn, lane = tid & 31, warp = tid >> 5;
   float* xl = xch + l * Z::XL;
   const int slot = (l + (t >> 1)) & 7;  // (z >> 1) & 7 == (t >> 1) & 7 for every z = t + p Tn of this thread
   auto tile_offset = [&](int tile) {
     const int c = tile % ncomp, r = tile / ncomp;
     return (((long long)c * ng + r % ng) * nky + r / ng) * (long long)TILE;
+  };
+  // Tiles are handed out by a global counter (not a fixed stride): a block that starts late, because its
+  // SM was still busy with the exchange kernel of the neighbouring component, simply processes fewer.
+  // One thread fetches the tile for a buffer, records it, and either starts its copy or, when the tiles
+  // have run out, completes the buffer's barrier by hand so that the waiting warps see the end.
+  auto arm = [&](int b) {
+    const int tile = atomicAdd(next_tile, 1);
+    tile_of[b] = tile;
+    if (tile < ntiles)
+      sb_bulk_load(tbuf + b * TILE, B + tile_offset(tile), TILE_BYTES, bars + b);
+    else
+      sb_mbar_arrive(bars + b);
   };
   if (tid == 0) {
     sb_mbar_init(bars + 0, 1);
@@ -750,16 +764,14 @@ __global__ void __launch_bounds__(SbZw<LOG2N>::NT, SbZw<LOG2N>::BLOCKS)
   }
   __syncthreads();
   if (tid == 0) {
-    int tile = blockIdx.x;
-    if (tile < ntiles) sb_bulk_load(tbuf, B + tile_offset(tile), TILE_BYTES, bars + 0);
-    tile += gridDim.x;
-    if (tile < ntiles) sb_bulk_load(tbuf + TILE, B + tile_offset(tile), TILE_BYTES, bars + 1);
+    arm(0);
+    arm(1);
   }
-  int k = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+  for (int k = 0;; ++k) {
     const int b = k & 1;
     C2<float>* tb = tbuf + b * TILE + slot;
     sb_mbar_wait_warp(bars + b, (unsigned)(k >> 1) & 1u);
+    if (tile_of[b] >= ntiles) break;
     C2<float> v[PT];
 #pragma unroll
     for (int p = 0; p < PT / 2; ++p) v[p] = tb[(t + p * Tn) * Z::LINES];
@@ -768,7 +780,7 @@ __global__ void __launch_bounds__(SbZw<LOG2N>::NT, SbZw<LOG2N>::BLOCKS)
     // (n floats per line, natural bin order) while the second register stage runs
     __syncwarp();
     {
-      const int r = tile / ncomp, kxg = r % ng, ky = r / ng;
+      const int r = tile_of[b] / ncomp, kxg = r % ng, ky = r / ng;  // (re-read: registers are scarce)
       const int m1 = ky <= (n1_full >> 1) ? ky : n1_full - ky;
       constexpr int LW = 32 / Tn;  // lines per warp
       const float* src = g5 + (((long long)m1 * ng + kxg) * Z::LINES + warp * LW) * N;
@@ -792,12 +804,9 @@ __global__ void __launch_bounds__(SbZw<LOG2N>::NT, SbZw<LOG2N>::BLOCKS)
       __threadfence_block();
       if ((atomicAdd(cnt + b, 1u) + 1) % Z::NW == 0) {  // last line of the tile: store it, re-arm the buffer
         __threadfence_block();
-        sb_bulk_store(B + tile_offset(tile), tbuf + b * TILE, TILE_BYTES);
-        const long long next = (long long)tile + 2LL * gridDim.x;
-        if (next < ntiles) {
-          sb_bulk_wait_read();
-          sb_bulk_load(tbuf + b * TILE, B + tile_offset((int)next), TILE_BYTES, bars + b);
-        }
+        sb_bulk_store(B + tile_offset(tile_of[b]), tbuf + b * TILE, TILE_BYTES);
+        sb_bulk_wait_read();
+        arm(b);
       }
     }
   }
@@ -872,6 +881,7 @@ struct SbFftState {
   // tile-contiguous layout of B + persistent bulk-copy z kernel (float, 3D, 2nz = 512 / 1024)
   bool zconv = false;
   int ng = 0;  // kx groups of 8 lines
+  int* tile_counter = nullptr;  // work counter of the persistent z kernel
   // optional per-launch timing (sb200_poisson_set_profiling): events around the five launches
   bool profile = false, have_times = false;
 #ifndef SB200_EMU
@@ -1109,29 +1119,35 @@ static int launch_zconv32(C2<float>* B, int ncomp, int ng, int nky, const C2<flo
 }
 template <int LOG2N>
 static int launch_zconvw(C2<float>* B, int ncomp, int ng, int nky, const C2<float>* tw, const float* g3,
-                         int n1_full, void* stream) {
+                         int n1_full, int* tile_counter, void* stream, int reserve_sms = 0) {
   using Z = SbZw<LOG2N>;
+  SB_REQUIRE(tile_counter != nullptr, "fft_zconvw: no tile counter");
+  sb_memset_async(tile_counter, 0, sizeof(int), stream);
   SB_KERNEL_ATTR_SMEM((sb_fft_zconvw_kernel<LOG2N>), Z::smem);
   const long long ntiles = (long long)ncomp * ng * nky;
   long long resident = 148LL * Z::BLOCKS;
 #ifndef SB200_EMU
   {
-    static long long cached = 0;
-    if (cached == 0) {
-      int dev = 0, sms = 0, per_sm = 0;
+    static int sms = 0, per_sm = 0;
+    if (sms == 0) {
+      int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_fft_zconvw_kernel<LOG2N>, Z::NT, Z::smem);
-      cached = (long long)sms * (per_sm > 0 ? per_sm : 1);
+      if (per_sm < 1) per_sm = 1;
     }
-    resident = cached;
+    // distributed solves overlap the peer-memory exchange of the neighbouring component with this kernel:
+    // a persistent grid that fills every SM would keep the push kernel out until it ends, so a few SMs
+    // stay free there
+    resident = (long long)(sms - (reserve_sms < sms ? reserve_sms : 0)) * per_sm;
   }
 #else
+  (void)reserve_sms;
   resident = 3;  // a few persistent "blocks", several tiles each
 #endif
   const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
   SB_LAUNCH_COOP((sb_fft_zconvw_kernel<LOG2N>), dim3(grid), dim3(Z::NT), Z::smem, stream, B, (int)ntiles, ncomp, ng,
-                 nky, tw, g3, n1_full);
+                 nky, tw, g3, n1_full, tile_counter);
   SB_CHECK_LAUNCH("fft_zconvw");
   return 0;
 }
@@ -1143,11 +1159,11 @@ static inline int sb_zconv_mode() {
 }
 template <typename T>
 static int launch_zconv(int log2n, C2<T>* B, int ncomp, int ng, int nky, const C2<T>* tw, const T* g2, int n1_full,
-                        void* stream) {
+                        int* tile_counter, void* stream, int reserve_sms = 0) {
   if constexpr (sizeof(T) == 4) {
     if (sb_zconv_mode() == 2) {
-      if (log2n == 9) return launch_zconvw<9>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
-      if (log2n == 10) return launch_zconvw<10>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
+      if (log2n == 9) return launch_zconvw<9>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, tile_counter, stream, reserve_sms);
+      if (log2n == 10) return launch_zconvw<10>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, tile_counter, stream, reserve_sms);
     }
     if (log2n == 9) return launch_zconv32<9>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
     if (log2n == 10) return launch_zconv32<10>((C2<float>*)B, ncomp, ng, nky, (const C2<float>*)tw, (const float*)g2, n1_full, stream);
@@ -1194,6 +1210,7 @@ static int fft_create_t(sb200_poisson* p, void* stream) {
     st->zconv = sb_zconv_mode() != 0 && sizeof(T) == 4 && p->dim == 3 && (st->pz.log2n == 9 || st->pz.log2n == 10) &&
                 sb_use_p32(1, st->pz.log2n);
   }
+  if (st->zconv) SB_REQUIRE(SB_DEV_ALLOC(st->tile_counter, 64), "fft backend: cannot allocate the tile counter");
   const size_t b_bytes = p->dim != 3 ? 0
                          : st->zconv ? sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * 8 * st->ng
                          : p->nranks == 1 ? sizeof(C2<T>) * 3 * (size_t)nz * 2 * ny * P
@@ -1281,7 +1298,7 @@ static int fft_solve_t(sb200_poisson* p, void* solution, const void* rhs, int nc
       lb.rot = sb_zconv_mode() == 2 ? 7 : 0;
       if ((e = launch_strided<T, 0>(st->py, st->A, la, st->B, lb, st->twy, none, stream))) return e;
       st->mark(2, stream);
-      if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * ny, stream))) return e;
+      if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * ny, st->tile_counter, stream))) return e;
       st->mark(3, stream);
       if ((e = launch_strided<T, 2>(st->py, st->B, lb, st->A, la, st->twy, none, stream))) return e;
       st->mark(4, stream);
@@ -1376,6 +1393,7 @@ static void fft_destroy_t(sb200_poisson* p) {
   if (st->B) SB_DEV_FREE(st->B);
   if (st->G) SB_DEV_FREE(st->G);
   if (st->G2) SB_DEV_FREE(st->G2);
+  if (st->tile_counter) SB_DEV_FREE(st->tile_counter);
 #ifndef SB200_EMU
   for (auto& ev : st->ev)
     if (ev) cudaEventDestroy(ev);
@@ -1450,7 +1468,8 @@ static int slab_spectral_t(sb200_poisson* p, void* recv, int ncomp, void* stream
     lb.s_grp = NKY * tile;
     lb.rot = sb_zconv_mode() == 2 ? 7 : 0;
     if ((e = launch_strided<T, 0>(st->py, (const C2<T>*)recv, sp.lr, st->B, lb, st->twy, none, stream))) return e;
-    if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * p->ny, stream)))
+    static const int reserve = getenv("SB200_ZCONV_RESERVE_SMS") ? atoi(getenv("SB200_ZCONV_RESERVE_SMS")) : 0;
+    if ((e = launch_zconv<T>(st->pz.log2n, st->B, ncomp, st->ng, (int)NKY, st->twz, st->G2, 2 * p->ny, st->tile_counter, stream, reserve)))
       return e;
     return launch_strided<T, 2>(st->py, st->B, lb, (C2<T>*)recv, sp.lr, st->twy, none, stream);
   }
