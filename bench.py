@@ -518,7 +518,8 @@ def main():
         z_bytes = (8 if zk.startswith("z_") else 20) * w_bytes * 3 * local_cells
         achieved = z_bytes / (acc[zk] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "fused z pass of the Poisson vector solve (forward FFT x Green x "
-                    "inverse FFT, in place): sb_fft_strided32_kernel / sb_fft_strided_kernel <MODE 1>",
+                    "inverse FFT, in place): sb_fft_zconvw_kernel (float, 2nz = 512 / 1024; one line per warp, "
+                    "bulk-copy tiles), sb_fft_strided_kernel <MODE 1> otherwise",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic(name) if world == 1 else None,
                     "peak_source": peak_src,
@@ -526,8 +527,9 @@ def main():
                     "algorithmic_bytes_per_cell": z_bytes / local_cells,
                     "share_of_step": acc[zk] / (ms_step if world == 1 else stage_ms["flow_step"]),
                     "per_gpu": world > 1,
-                    "note": "FP32-issue and HBM co-limited (radix-16/32 butterflies, ~33 lane-ops per complex "
-                            "point and transform); see profiles/"}
+                    "note": "bound by FP32 issue, not by HBM: two 2nz-point transforms per line = ~7 FP32 "
+                            "lane-operations per byte (FMA pipe 66 % busy, DRAM 1.19 x algorithmic); see "
+                            "DESIGN.md 'Fused z pass' and profiles/r02_ncu_zconvw_512.txt"}
     nvlink = None
     if world > 1 and "poisson_all_to_all_z_to_kx" in stage_ms:
         # each all-to-all moves the x-pass output (nx/2 + 1 complex bins per row = 2 W per cell) of this

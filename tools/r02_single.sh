@@ -18,6 +18,6 @@ done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file "$out/${tag}_launches_fsi512.csv" \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python tools/agg_launches.py "$out/${tag}_launches_fsi512.csv" 18 | grep -v Greens
-ncu --set full --import-source on --clock-control none -k regex:"zconv32|fused_v2|strided32_kernel|velocity_vec4|x_r2c|x_c2r|ib_" \
+ncu --set full --import-source on --clock-control none -k regex:"zconvw|fused_v2|strided32_kernel|velocity_vec4|x_r2c|x_c2r|ib_" \
   -s 40 -c 14 -o "$out/${tag}_prof_fsi512" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ls -la "$out/${tag}_prof_fsi512.ncu-rep"
