@@ -106,14 +106,14 @@ __global__ void __launch_bounds__(512)
 // wait (on the stream) until the n flags of this rank's buffer have reached `epoch`: every source rank
 // has finished writing its block.  A bounded spin: after ~2 s without progress the kernel gives up and
 // raises *error instead of hanging the device.
-__global__ void sb_wait_flags_kernel(const int* flags, int n, int epoch, int* error) {
+__global__ void sb_wait_flags_kernel(const int* flags, int n, int epoch, int* error, long long limit_ticks) {
   const int k = threadIdx.x;
   if (k >= n) return;
 #ifndef SB200_EMU
   const volatile int* f = flags + k;
   const long long t0 = clock64();
   while (*f < epoch) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > limit_ticks) {
       *error = 1;
       break;
     }
@@ -148,7 +148,10 @@ extern "C" int sb200_peer_push_blocks(int n, void* const* dst, const void* const
 
 extern "C" int sb200_peer_wait_flags(const void* flags, int n, int epoch, void* error_flag, void* stream) {
   SB_REQUIRE(flags && error_flag && n >= 1 && n <= 32, "peer_wait_flags: bad arguments");
-  SB_LAUNCH(sb_wait_flags_kernel, dim3(1), dim3(32), 0, stream, (const int*)flags, n, epoch, (int*)error_flag);
+  // ~2 s by default; SB200_PEER_WAIT_S raises it (ranks that time-share ONE device, as in
+  // tests/test_gpu_ranks_on_one_device.py, hand the GPU to each other one time slice at a time)
+  static const long long limit = (long long)(2.0e9 * (getenv("SB200_PEER_WAIT_S") ? atof(getenv("SB200_PEER_WAIT_S")) : 2.0));
+  SB_LAUNCH(sb_wait_flags_kernel, dim3(1), dim3(32), 0, stream, (const int*)flags, n, epoch, (int*)error_flag, limit);
   SB_CHECK_LAUNCH("peer_wait_flags");
   return 0;
 }
@@ -164,6 +167,10 @@ extern "C" int sb200_peer_alloc(int64_t bytes, void** ptr_out) {
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, (size_t)bytes);
   if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  // cudaMemset of device memory only ENQUEUES the fill: without this, a peer that maps the buffer can
+  // raise an epoch flag in it before the fill runs and have it wiped (seen as a lost halo signal with
+  // several ranks on one device, tests/test_gpu_ranks_on_one_device.py)
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     sb_set_error("peer_alloc: %s", cudaGetErrorString(e));
     return -2;

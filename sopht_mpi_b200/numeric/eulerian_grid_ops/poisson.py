@@ -135,7 +135,7 @@ class _UnboundedPoissonSolver:
                               torch.zeros(glob_shape, dtype=local.dtype, device=local.device),
                               torch.zeros(glob_shape, dtype=local.dtype, device=local.device))
         gathered, g_rhs, g_sol = self._rep_bufs
-        dist.all_gather_into_tensor(gathered, local)
+        dist.all_gather_into_tensor(gathered.view(-1), local.view(-1))  # (flat: the form every backend takes)
         n_lead = local.shape[1]
         # (P, ncomp, n_lead_local, ...) -> (ncomp, P * n_lead_local, ...): slabs stack along the leading axis
         g_rhs[inner].copy_(gathered.transpose(0, 1).reshape((ncomp, size * n_lead) + tuple(local.shape[2:])))
