@@ -41,27 +41,32 @@ SB_D double sb_block_reduce(double v) {
 
 // mode 0: max of sum_c |f_c| ; 1: signed max over comps ; 2: sum of squares
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) sb_reduce_kernel(SbGeom g, const T* f, int ncomp, void* out) {
+__global__ void __launch_bounds__(256) sb_reduce_kernel(SbGeom g, const T* f, int ncomp, void* out, int zchunk) {
+  // a thread owns one (y,x) column and marches over zchunk planes (independent loads in flight, one block
+  // reduction + one atomic per block instead of one per 256 cells)
   const long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int z = blockIdx.y;
   const int y = pidx < g.plane ? (int)(pidx / g.mx) : g.my;
   const int x = pidx < g.plane ? (int)(pidx - (long long)y * g.mx) : g.mx;
+  const int zb = blockIdx.y * zchunk, ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
   double v = MODE == 2 ? 0.0 : -1.0e300;
-  if (x < g.mx && y < g.my && z < g.mz && g.interior(z, y, x)) {
-    const long long i = g.idx(z, y, x);
-    if (MODE == 0) {
-      T s = 0;
-      for (int c = 0; c < ncomp; ++c) s += fabs(f[i + c * g.vol]);
-      v = (double)s;
-    } else if (MODE == 1) {
-      for (int c = 0; c < ncomp; ++c) {
-        const double t = (double)f[i + c * g.vol];
-        v = t > v ? t : v;
-      }
-    } else {
-      for (int c = 0; c < ncomp; ++c) {
-        const double t = (double)f[i + c * g.vol];
-        v += t * t;
+  if (x < g.mx && y < g.my) {
+    for (int z = zb; z < ze; ++z) {
+      if (!g.interior(z, y, x)) continue;
+      const long long i = g.idx(z, y, x);
+      if (MODE == 0) {
+        T s = 0;
+        for (int c = 0; c < ncomp; ++c) s += fabs(f[i + c * g.vol]);
+        v = (double)s > v ? (double)s : v;
+      } else if (MODE == 1) {
+        for (int c = 0; c < ncomp; ++c) {
+          const double t = (double)f[i + c * g.vol];
+          v = t > v ? t : v;
+        }
+      } else {
+        for (int c = 0; c < ncomp; ++c) {
+          const double t = (double)f[i + c * g.vol];
+          v += t * t;
+        }
       }
     }
   }
@@ -90,13 +95,14 @@ static int sb_reduce(const sb200_grid_t* gr, const void* field, int ncomp, void*
   int e = sb_memset_async(out, 0, 8, stream);
   SB_REQUIRE(e == 0, "reduce: memset failed");
   dim3 block(256);
-  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)g.mz);
+  const int zchunk = g.mz >= 64 ? 16 : (g.mz >= 8 ? 4 : 1);
+  dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)((g.mz + zchunk - 1) / zchunk));
   if (gr->dtype == SB200_F32) {
     SB_LAUNCH_COOP((sb_reduce_kernel<float, MODE>), grid, block, 0, stream, g, (const float*)field,
-                   ncomp, out);
+                   ncomp, out, zchunk);
   } else {
     SB_LAUNCH_COOP((sb_reduce_kernel<double, MODE>), grid, block, 0, stream, g, (const double*)field,
-                   ncomp, out);
+                   ncomp, out, zchunk);
   }
   SB_CHECK_LAUNCH("reduce");
   if (MODE != 2) {
