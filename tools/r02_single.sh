@@ -4,7 +4,7 @@ set -u
 tag=${1:-r02x}
 out=gpurun_out
 mkdir -p "$out"
-python tools/ubench/push_local.py 2>&1 | tail -6
+true
 python -m pytest tests -m gpu -q > "$out/${tag}_gpu_tests.log" 2>&1
 tail -8 "$out/${tag}_gpu_tests.log"
 python bench.py --steps 10 --no-cpu-baseline > "$out/${tag}_bench_fsi512.json" 2> "$out/${tag}_bench_fsi512.err"
