@@ -3,6 +3,7 @@ ordering (``sopht_mpi/simulator/flow/flow_simulators_mpi_3d.py:24-476``); fields
 live on the GPU, every operator is a ``libsophtb200`` kernel.
 """
 import ctypes
+import os
 from typing import Callable
 
 import numpy as np
@@ -24,9 +25,12 @@ from ...numeric.eulerian_grid_ops import (
 )
 from ...numeric.eulerian_grid_ops.ops import OpContext
 from ...utils import MPI, MPIConstruct3D, MPIGhostCommunicator3D, logger
+from ...utils.deferred import DeferredScalar
 from ...utils.device import current_stream_ptr, dptr, zeros, zeros_like
 from ...utils.precision import get_test_tol
 from .flow_simulator_common import FlowSimulatorCommon
+
+_EAGER_DT = os.environ.get("SB200_EAGER_DT", "0") == "1"
 
 
 class UnboundedFlowSimulator3D(FlowSimulatorCommon):
@@ -149,6 +153,7 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
         self._max_abs_vel_glob = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._max_abs_vel_host = torch.zeros(1, dtype=torch.float64, pin_memory=torch.cuda.is_available())
         self._max_abs_vel_event = torch.cuda.Event() if torch.cuda.is_available() else None
+        self._pending_dt = None
         self._reduce_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
 
     def compile_kernels(self):
@@ -315,11 +320,14 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
         self._publish_max_abs_vel()
 
     def _publish_max_abs_vel(self):
-        """Reduce max |u| over the ranks and start its copy to the host behind the producing kernel, so
+        """(A deferred timestep that nobody has read yet is read first: the pinned scalar is about to be
+        overwritten.)  Reduce max |u| over the ranks and start its copy to the host behind the producing kernel, so
         that the next compute_stable_timestep only waits for an event.  dt = min over ranks of a
         decreasing function of the local maximum = that function of the global maximum: one NCCL
         all-reduce (MAX) of the device scalar replaces the reference's host allreduce(MIN) of dt
         (flow_simulators_mpi_3d.py:447-448)."""
+        if self._pending_dt is not None:
+            self._pending_dt._get()
         self._max_abs_vel_glob.copy_(self._max_abs_vel_dev)
         if self._ctx.distributed:
             import torch.distributed as dist
@@ -444,13 +452,25 @@ class UnboundedFlowSimulator3D(FlowSimulatorCommon):
                      dptr(self._max_abs_vel_dev), ctx.stream())
             # (not cached: only the fused velocity sweep knows that it was the last writer)
             self._publish_max_abs_vel()
-        self._max_abs_vel_event.synchronize()
-        max_vel = self.real_t(float(self._max_abs_vel_host[0]))
-        dt = min(
-            self.CFL * self.dx / (max_vel + tol),
-            0.9 * self.dx ** 2 / (2 * self.grid_dim) / (self.kinematic_viscosity + tol),
-        )
-        return dt * dt_prefac
+
+        def resolve():
+            self._max_abs_vel_event.synchronize()
+            max_vel = self.real_t(float(self._max_abs_vel_host[0]))
+            dt = min(
+                self.CFL * self.dx / (max_vel + tol),
+                0.9 * self.dx ** 2 / (2 * self.grid_dim) / (self.kinematic_viscosity + tol),
+            )
+            self._pending_dt = None
+            return dt * dt_prefac
+
+        if _EAGER_DT:
+            return resolve()
+        # read when first used (utils/deferred.py): the caller's next kernels, the interaction in the
+        # reference's step order, are enqueued before the host waits for this value
+        if self._pending_dt is not None:
+            self._pending_dt._get()
+        self._pending_dt = DeferredScalar(resolve)
+        return self._pending_dt
 
     def get_vorticity_divergence_l2_norm(self):
         """reference :451-469"""
