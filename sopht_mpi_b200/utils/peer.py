@@ -10,9 +10,9 @@ the destination's memory, and a one-warp kernel on the destination's stream wait
 (bounded spin), so no collective sits on the critical path.  Replaces the MPI ``Alltoallw`` inside
 mpi4py-fft's transposes (reference ``poisson_solver_3d/fft_mpi_3d.py:27-48``).
 
-``SB200_EXCHANGE`` selects the transport for measurements: ``push`` (default), ``push-nccl`` (push kernel +
-a one-element NCCL all-reduce as the barrier), ``copy`` (one ``cudaMemcpyPeerAsync`` per destination on
-the stream + all-reduce, round 1), ``nccl`` (all-to-all).  If CUDA IPC is not available (different
+``SB200_EXCHANGE`` selects the transport: ``push`` (default on more than 4 ranks), ``copy`` (one
+``cudaMemcpyPeerAsync`` per destination on the stream + a one-element all-reduce as the barrier; default on
+2 and 4 ranks), ``push-nccl`` (push kernel + the all-reduce barrier), ``nccl`` (all-to-all).  If CUDA IPC is not available (different
 nodes, no peer access) the exchange falls back to NCCL.
 """
 import ctypes
@@ -39,7 +39,10 @@ class PeerExchange:
     def __init__(self, n_buffers, n_float32, device, rank, nranks, use_peer_copies=True):
         self.rank, self.nranks, self.device = rank, nranks, device
         self.n_buffers, self.n_float32 = n_buffers, int(n_float32)
-        self.transport = os.environ.get("SB200_EXCHANGE", "push")
+        # measured on the 512^3 step (profiles/r02_exchange_transports.txt): inside the component pipeline
+        # the copy engines win on 2 and 4 ranks (few, large copies; no SM or load/store-path interference with
+        # the transform kernels the exchange overlaps), the push kernel on 8 (seven destinations at once)
+        self.transport = os.environ.get("SB200_EXCHANGE") or ("copy" if nranks <= 4 else "push")
         # thread blocks per destination: ~32 blocks of 512 threads saturate one NVLink port pair
         # (tools/ubench/peer_copy.py: 8 -> 364, 16 -> 630, 32 -> 658 GB/s); with P - 1 destinations in
         # flight the egress limit is shared, so fewer blocks per destination leave more SMs to the
