@@ -652,6 +652,9 @@ def main():
         import gc
 
         solver.close()
+        halo = getattr(sim.mpi_construct, "_peer_halo", None)
+        if halo is not None:
+            halo.close()
         del solver, sim, interactor
         gc.collect()
         torch.cuda.ipc_collect()

@@ -40,35 +40,45 @@ SB_D double sb_block_reduce(double v) {
 }
 
 // mode 0: max of sum_c |f_c| ; 1: signed max over comps ; 2: sum of squares
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256) sb_reduce_kernel(SbGeom g, const T* f, int ncomp, void* out, int zchunk) {
-  // a thread owns one (y,x) column and marches over zchunk planes (independent loads in flight, one block
-  // reduction + one atomic per block instead of one per 256 cells)
+template <typename T, int MODE, int NCOMP>
+__global__ void __launch_bounds__(256) sb_reduce_kernel(SbGeom g, const T* __restrict__ f, int ncomp_rt, void* out,
+                                                        int zchunk) {
+  // a thread owns one interior (y,x) column and marches over zchunk planes: the (y,x) test is done once,
+  // the loads of the unrolled march are independent, one block reduction + one atomic per block
+  const int ncomp = NCOMP > 0 ? NCOMP : ncomp_rt;
   const long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int y = pidx < g.plane ? (int)(pidx / g.mx) : g.my;
   const int x = pidx < g.plane ? (int)(pidx - (long long)y * g.mx) : g.mx;
-  const int zb = blockIdx.y * zchunk, ze = zb + zchunk < g.mz ? zb + zchunk : g.mz;
+  const int zlo = g.dim == 3 ? g.gs : 0, zhi = g.dim == 3 ? g.mz - g.gs : 1;  // interior planes
+  int zb = blockIdx.y * zchunk, ze = zb + zchunk;
+  zb = zb > zlo ? zb : zlo;
+  ze = ze < zhi ? ze : zhi;
   double v = MODE == 2 ? 0.0 : -1.0e300;
-  if (x < g.mx && y < g.my) {
-    for (int z = zb; z < ze; ++z) {
-      if (!g.interior(z, y, x)) continue;
-      const long long i = g.idx(z, y, x);
+  if (x >= g.gs && x < g.mx - g.gs && y >= g.gs && y < g.my - g.gs) {
+    const T* p = f + g.idx(zb, y, x);
+    T acc = sizeof(T) == 4 ? T(-3.402823466e38) : T(-1.7976931348623157e308);  // lowest finite value
+#pragma unroll 4
+    for (int z = zb; z < ze; ++z, p += g.plane) {
       if (MODE == 0) {
         T s = 0;
-        for (int c = 0; c < ncomp; ++c) s += fabs(f[i + c * g.vol]);
-        v = (double)s > v ? (double)s : v;
+#pragma unroll
+        for (int c = 0; c < ncomp; ++c) s += fabs(p[c * g.vol]);
+        acc = s > acc ? s : acc;
       } else if (MODE == 1) {
+#pragma unroll
         for (int c = 0; c < ncomp; ++c) {
-          const double t = (double)f[i + c * g.vol];
-          v = t > v ? t : v;
+          const T t = p[c * g.vol];
+          acc = t > acc ? t : acc;
         }
       } else {
+#pragma unroll
         for (int c = 0; c < ncomp; ++c) {
-          const double t = (double)f[i + c * g.vol];
+          const double t = (double)p[c * g.vol];
           v += t * t;
         }
       }
     }
+    if (MODE != 2 && ze > zb) v = (double)acc;
   }
   v = sb_block_reduce<MODE != 2>(v);
   const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
@@ -97,13 +107,14 @@ static int sb_reduce(const sb200_grid_t* gr, const void* field, int ncomp, void*
   dim3 block(256);
   const int zchunk = g.mz >= 64 ? 16 : (g.mz >= 8 ? 4 : 1);
   dim3 grid((unsigned)((g.plane + 255) / 256), (unsigned)((g.mz + zchunk - 1) / zchunk));
+#define SB_LAUNCH_REDUCE(T, NC) \
+  SB_LAUNCH_COOP((sb_reduce_kernel<T, MODE, NC>), grid, block, 0, stream, g, (const T*)field, ncomp, out, zchunk)
   if (gr->dtype == SB200_F32) {
-    SB_LAUNCH_COOP((sb_reduce_kernel<float, MODE>), grid, block, 0, stream, g, (const float*)field,
-                   ncomp, out, zchunk);
+    if (ncomp == 3) SB_LAUNCH_REDUCE(float, 3); else if (ncomp == 1) SB_LAUNCH_REDUCE(float, 1); else SB_LAUNCH_REDUCE(float, 0);
   } else {
-    SB_LAUNCH_COOP((sb_reduce_kernel<double, MODE>), grid, block, 0, stream, g, (const double*)field,
-                   ncomp, out, zchunk);
+    if (ncomp == 3) SB_LAUNCH_REDUCE(double, 3); else if (ncomp == 1) SB_LAUNCH_REDUCE(double, 1); else SB_LAUNCH_REDUCE(double, 0);
   }
+#undef SB_LAUNCH_REDUCE
   SB_CHECK_LAUNCH("reduce");
   if (MODE != 2) {
     SB_LAUNCH(sb_decode_key_kernel, dim3(1), dim3(32), 0, stream, out);

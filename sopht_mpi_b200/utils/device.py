@@ -199,6 +199,11 @@ class Staged:
         if x is None:
             return None
         if isinstance(x, DeviceField):
+            if out:
+                # an operator is about to rewrite this field on the device: whatever was derived from its
+                # old contents (the cached max |u| of the stable timestep, "ghost planes are current")
+                # is stale, exactly as after a host-side write
+                x._touch()
             x = x.tensor
         if isinstance(x, torch.Tensor):
             if not x.is_contiguous():
