@@ -44,6 +44,12 @@ class DeferredScalar:
             self._fn = None
         return self._val
 
+    def __getattr__(self, name):
+        # everything else a numpy scalar offers (.item(), .dtype, .astype ...) comes from the value itself
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return getattr(self._get(), name)
+
     # conversions
     def __float__(self):
         return float(self._get())

@@ -21,5 +21,11 @@ def test_deferred_scalar_resolves_once_and_behaves_like_a_number():
     t = 0.0
     t += d
     assert t == 0.125 and len(calls) == 1
+    assert d.item() == 0.125 and d.dtype == np.float32 and d.astype(np.float64) == 0.125  # numpy scalar methods
+    assert np.isclose(d, 0.125) and not np.isnan(d)
+    import copy
+    import math
+
+    assert math.sqrt(d) == math.sqrt(0.125) and copy.copy(d) == 0.125
     e = DeferredScalar(lambda: np.float64(3.0))
     assert d * e == 0.375 and e ** 2 == 9 and -e == -3 and abs(-e) == 3 and 2 ** e == 8
