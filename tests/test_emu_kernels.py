@@ -315,6 +315,7 @@ def test_ib_kernels_against_reference_golden(path):
     (np.float32, (8, 64, 16)), (np.float64, (128, 8, 16)), (np.float32, (8, 8, 1024)),
     (np.float32, (128, 8, 16)), (np.float32, (8, 128, 16)), (np.float32, (256, 8, 16)),
     (np.float32, (8, 256, 16)), (np.float32, (512, 8, 16)), (np.float64, (8, 128, 16)),
+    (np.float32, (8, 512, 16)),
 ], ids=lambda v: str(v) if isinstance(v, tuple) else v.__name__)
 def test_pruned_fft_poisson_pipeline_3d(real_t, n):
     """backend 1 (in-kernel pruned FFT pipeline): every Stockham plan shape up to n = 1024
