@@ -219,9 +219,16 @@ __global__ void __launch_bounds__(256)
     for (int e = 0; e < 4; ++e) {
       const long long i = c * SB_CHUNK + e * 256 + threadIdx.x;
       if (i >= g.vol) continue;
-      const int z = (int)(i / g.plane);
-      const long long r = i - (long long)z * g.plane;
-      const int y = (int)(r / g.mx), x = (int)(r - (long long)y * g.mx);
+      int z, y, x;
+      if (g.vol < (1LL << 31)) {  // 32-bit divisions (a 512^3 slab has 1.4e8 cells)
+        const unsigned ui = (unsigned)i, uz = ui / (unsigned)g.plane, r = ui - uz * (unsigned)g.plane;
+        const unsigned uy = r / (unsigned)g.mx;
+        z = (int)uz, y = (int)uy, x = (int)(r - uy * (unsigned)g.mx);
+      } else {
+        z = (int)(i / g.plane);
+        const long long r = i - (long long)z * g.plane;
+        y = (int)(r / g.mx), x = (int)(r - (long long)y * g.mx);
+      }
       op(g, z, y, x);
     }
   }
