@@ -8,6 +8,8 @@ anything of the new step.  The interaction does not need dt, so with the deferre
 queued behind the previous step and the wait (``float(dt)`` inside ``time_step``) finds work in flight.
 The object resolves itself on any arithmetic, comparison, conversion or formatting, and yields exactly
 the numpy scalar the eager code path would have returned; ``SB200_EAGER_DT=1`` switches the deferral off.
+(The 2D simulator stays eager: its 512 x 256 step is bound by host launches, there is no GPU idle time to
+win back, and the deferral's own Python costs 0.02 ms of a 0.235 ms step: measured 0.255 ms.)
 """
 import operator
 
